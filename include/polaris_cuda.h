@@ -1,0 +1,206 @@
+/*
+ * polaris_cuda.h -- C ABI of libpolaris_cuda.so, the B200 (sm_100a) path-tracing
+ * backend for polaris.
+ *
+ * This is the drop-in boundary for the one hot path of the reference: the Go
+ * interface `tracer.Tracer` (reference tracer/tracer.go:80-111) as implemented by
+ * `tracer/opencl.Tracer` (reference tracer/opencl/tracer.go).  Every entry point
+ * below names the reference method it replaces.  A Go `tracer/cuda` package binds
+ * these through cgo (see INTEGRATION.md and go/tracer/cuda/); tests and bench.py
+ * bind them through ctypes (polaris_b200/_lib.py).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; the caller owns every host pointer, the
+ *    library copies during the call and never retains it (the reference instead
+ *    relies on CL_MEM_USE_HOST_PTR, tracer/opencl/device/buffer.go:98-104);
+ *  - every function that can fail returns 0 on success or a pc_status code;
+ *    pc_last_error() gives the message for the calling handle;
+ *  - calls on one handle may come from any OS thread (goroutines migrate); the
+ *    library takes a per-handle mutex and does cudaSetDevice on entry;
+ *  - all scene structs are the byte layouts of reference
+ *    asset/scene/optimized_scene.go:25-165 == tracer/opencl/CL/types.cl.
+ */
+#ifndef POLARIS_CUDA_H
+#define POLARIS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_ABI_VERSION 1
+
+/* ---- status codes (mirror tracer/opencl/errors.go:5-22 where one exists) ---- */
+typedef enum pc_status {
+    PC_OK = 0,
+    PC_ERR_INVALID_ARGUMENT = 1,   /* ErrInvalidChangeData / ErrInvalidOption      */
+    PC_ERR_NO_DEVICE = 2,          /* ErrContextCreationFailed                     */
+    PC_ERR_ALLOC = 3,              /* ErrAllocatingBuffer                          */
+    PC_ERR_COPY_TO_DEVICE = 4,     /* ErrCopyingDataToDevice                       */
+    PC_ERR_COPY_TO_HOST = 5,       /* ErrCopyingDataToHost                         */
+    PC_ERR_KERNEL = 6,             /* ErrKernelExecutionFailed (sticky: handle dead)*/
+    PC_ERR_NO_SCENE_DATA = 7,      /* ErrNoSceneData (errors.go:21)                */
+    PC_ERR_NO_FRAME = 8,           /* Trace before FrameDimensions were committed  */
+    PC_ERR_UNSUPPORTED_TRACER = 9, /* MergeOutput: "unsupported tracer instance"   */
+    PC_ERR_STACK_DEPTH = 10,       /* scene BVH deeper than the traversal stack    */
+    PC_ERR_BAD_SCENE = 11,         /* scene view fails validation at upload        */
+    PC_ERR_PEER_ACCESS = 12        /* cross-device merge without a P2P path        */
+} pc_status;
+
+/* Opaque tracer handle == one tracer/opencl.Tracer bound to one CUDA device. */
+typedef struct pc_tracer pc_tracer;
+
+/* tracer.BlockRequest, reference tracer/tracer.go:6-34 (12 x 4 bytes, same order). */
+typedef struct pc_block_request {
+    uint32_t frame_w, frame_h;
+    uint32_t block_x, block_y, block_w, block_h;
+    uint32_t samples_per_pixel;
+    uint32_t num_bounces;
+    uint32_t min_bounces_for_rr;
+    float    exposure;
+    uint32_t seed;
+    uint32_t accumulated_samples;
+} pc_block_request;
+
+/* tracer.Stats, reference tracer/tracer.go:37-47 (durations in nanoseconds) plus
+ * device-side counters the reference never exposes (pipeline.go:278-282 is unused). */
+typedef struct pc_stats {
+    uint32_t block_w, block_h;
+    uint64_t update_time_ns;
+    uint64_t render_time_ns;        /* host wall time of the last pc_trace         */
+    uint64_t device_time_ns;        /* CUDA-event time of the last pc_trace        */
+    uint64_t query_rays;            /* closest-hit rays launched (primary+indirect)*/
+    uint64_t occlusion_rays;        /* any-hit rays launched                       */
+    uint64_t kernel_launches;       /* kernels launched by the last pc_trace       */
+    /* valid only when PC_OPT_COUNTERS is on: */
+    uint64_t nodes_tested;          /* BVH inner-node visits (2 child boxes each)  */
+    uint64_t tris_tested;
+    uint64_t instances_entered;
+    uint64_t shaded_hits;
+    uint64_t occlusion_emitted;
+    uint64_t indirect_emitted;
+    uint64_t unoccluded;
+    uint64_t missed_query_rays;
+} pc_stats;
+
+/* scene.Scene flat buffers, reference asset/scene/optimized_scene.go:167-190, in the
+ * order tracer/opencl/buffers.go:180-191 uploads them. Byte sizes, not counts. */
+typedef struct pc_scene_view {
+    const void *bvh_nodes;        uint64_t bvh_nodes_bytes;        /* 32 B BvhNode          */
+    const void *mesh_instances;   uint64_t mesh_instances_bytes;   /* 80 B MeshInstance     */
+    const void *material_nodes;   uint64_t material_nodes_bytes;   /* 64 B MaterialNode     */
+    const void *texture_data;     uint64_t texture_data_bytes;     /* raw bytes             */
+    const void *texture_metadata; uint64_t texture_metadata_bytes; /* 16 B TextureMetadata  */
+    const void *vertices;         uint64_t vertices_bytes;         /* float4 per vertex     */
+    const void *normals;          uint64_t normals_bytes;          /* float4 per vertex     */
+    const void *uvs;              uint64_t uvs_bytes;              /* float2 per vertex     */
+    const void *material_indices; uint64_t material_indices_bytes; /* uint32 per triangle   */
+    const void *emissives;        uint64_t emissives_bytes;        /* 80 B EmissivePrimitive*/
+    int32_t scene_diffuse_mat_index;    /* -1 when the scene has no background material */
+    int32_t scene_emissive_mat_index;
+} pc_scene_view;
+
+/* pc_read_buffer selectors: the reference's bufferSet (tracer/opencl/buffers.go:21-70). */
+typedef enum pc_buffer {
+    PC_BUF_RAYS0 = 0, PC_BUF_RAYS1 = 1, PC_BUF_RAYS2 = 2,   /* 32 B Ray               */
+    PC_BUF_PATHS = 3,                                       /* 32 B Path              */
+    PC_BUF_HIT_FLAGS = 4,                                   /* uint32                 */
+    PC_BUF_INTERSECTIONS = 5,                               /* 32 B Intersection      */
+    PC_BUF_EMISSIVE_SAMPLES = 6,                            /* float3 in 16 B         */
+    PC_BUF_TRACE_ACCUMULATOR = 7,                           /* float3 in 16 B / pixel */
+    PC_BUF_FRAME_ACCUMULATOR = 8,
+    PC_BUF_FRAME_BUFFER = 9,                                /* RGBA8                  */
+    PC_BUF_RAY_COUNTERS = 10                                /* 3 x int32              */
+} pc_buffer;
+
+typedef enum pc_option {
+    PC_OPT_COUNTERS = 0,        /* 1: count nodes/tris/instances per ray (slower)         */
+    PC_OPT_PRIMARY_PACKETS = 1, /* 1 (default): warp-packet traversal for primary rays,
+                                   0: per-ray traversal (what the reference does on CPU
+                                   devices, pipeline.go:107-111)                          */
+    PC_OPT_REFERENCE_ORDER = 2, /* 1: left-first traversal without closest-hit culling,
+                                   i.e. literally intersect.cl:184-347; default 0         */
+    PC_OPT_USE_GRAPH = 3,       /* 1 (default): replay one CUDA graph per sample          */
+    PC_OPT_FIX_Q4 = 4           /* 1 (default): emissive hits accumulate at pixelIndex;
+                                   0: at the ray's path index like pt_integrator.cl:106   */
+} pc_option;
+
+/* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */
+int pc_abi_version(void);
+int pc_device_count(void);
+/* name (<= cap bytes incl. NUL), SM count, max SM clock in MHz, and the reference's speed
+ * estimate computeUnits*clockMHz/1000 (tracer/opencl/device/device.go:209-222). */
+int pc_device_info(int ordinal, char *name, size_t cap, uint32_t *sm_count,
+                   uint32_t *clock_mhz, uint32_t *speed);
+
+/* ---- lifecycle: opencl.NewTracer + Tracer.Init (tracer.go:58-117) / Tracer.Close (:120-142) ---- */
+int  pc_create(int ordinal, const char *id, pc_tracer **out);
+void pc_destroy(pc_tracer *tr);                 /* idempotent on NULL */
+const char *pc_id(const pc_tracer *tr);         /* Tracer.Id    (tracer.go:75) */
+uint32_t    pc_flags(const pc_tracer *tr);      /* Tracer.Flags (tracer.go:80): Local = 1 */
+uint32_t    pc_speed(const pc_tracer *tr);      /* Tracer.Speed (tracer.go:90) */
+const char *pc_last_error(const pc_tracer *tr); /* NULL handle: creation error of this thread */
+
+/* ---- Tracer.UpdateState(Synchronous, ...) payloads (tracer.go:150-191) ---- */
+/* FrameDimensions -> bufferSet.Resize (buffers.go:127-175) */
+int pc_resize(pc_tracer *tr, uint32_t frame_w, uint32_t frame_h);
+/* SceneData -> bufferSet.UploadSceneData (buffers.go:177-201); also derives the
+ * 16-byte-aligned traversal layout and checks the BVH depth against the stack. */
+int pc_upload_scene(pc_tracer *tr, const pc_scene_view *scene);
+/* CameraData: camera.Position and camera.Frustrum (tracer.go:176-179);
+ * frustum rows are TL, TR, BL, BR as xyzw (asset/scene/camera.go:121-141). */
+int pc_set_camera(pc_tracer *tr, const float eye[3], const float frustum[16]);
+int pc_set_option(pc_tracer *tr, int option, int value);
+
+/* ---- Tracer.Trace (tracer.go:194-247) ----
+ * Traces rows [block_y, block_y+block_h) x frame_w, samples_per_pixel samples.
+ * seeds: (1 + num_bounces) per sample in the order the reference draws them from
+ * math/rand: the camera seed (tracer.go:222) then one shadeHits seed per bounce
+ * (pipeline.go:146).  seeds == NULL: the library draws them from its own generator.
+ * Like the reference, req->seed and req->accumulated_samples are updated in place.
+ * stats may be NULL. The call returns after the device finished the block. */
+int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds,
+             size_t n_seeds, pc_stats *stats);
+/* Tracer.Stats (tracer.go:145) for the last pc_trace. */
+int pc_get_stats(pc_tracer *tr, pc_stats *stats);
+
+/* ---- Tracer.MergeOutput (tracer.go:279-286): dst.frameAccumulator[rows] += src.traceAccumulator[rows].
+ * dst and src may live on different GPUs (peer loads over NVLink). Returns without
+ * waiting for completion, like Exec1DNoWait (resources.go:119); safe to call
+ * concurrently for one dst. */
+int pc_merge_output(pc_tracer *dst, pc_tracer *src, const pc_block_request *req);
+/* Same merge when the source rows arrive as a host or device buffer produced by another
+ * process (one process per GPU, rows gathered with NCCL): rows points at
+ * block_w*block_h float4 values for the block of req. is_device: 0 host, 1 device ptr. */
+int pc_merge_rows(pc_tracer *dst, const void *rows, int is_device, const pc_block_request *req);
+/* Device pointer + byte length of the block rows of this tracer's trace accumulator
+ * (what a gather sends). */
+int pc_trace_rows(pc_tracer *tr, const pc_block_request *req, void **device_ptr, uint64_t *bytes);
+
+/* ---- Tracer.SyncFramebuffer (tracer.go:250-276): wait, tonemap (hdr.cl:5-28) rows
+ * [0, block_h) and optionally copy the RGBA8 frame (frame_w*frame_h*4 bytes) to rgba_out
+ * (what SaveFrameBuffer / CopyFrameBufferToOpenGLTexture read, pipeline.go:216-256). */
+int pc_sync_framebuffer(pc_tracer *tr, const pc_block_request *req, uint8_t *rgba_out);
+
+/* ---- test / oracle hooks ---- */
+int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes);
+/* Upload n rays (32 B each) into rays0 and run one intersection kernel on them:
+ * mode 0 = rayIntersectionQuery, 1 = rayIntersectionTest, 2 = packet query.
+ * out_flags: n uint32; out_hits: n 32-B Intersection records (ignored for mode 1). */
+int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode,
+                       uint32_t *out_flags, void *out_hits);
+/* Evaluate the device BxDF functions (bxdf.cl:29-105) for n records; see
+ * polaris_b200/_lib.py for the 64-byte input / 48-byte output record layouts. */
+int pc_debug_bxdf(pc_tracer *tr, const void *in_records, uint32_t n, void *out_records);
+/* Device RNG (random_sampler.cl:7-16): n states (uint2) -> draws x n x float2 + final states. */
+int pc_debug_rng(pc_tracer *tr, uint32_t *states_inout, uint32_t n, uint32_t draws, float *out);
+/* Device tonemap (hdr.cl:5-28) of n float4 accumulators -> n RGBA8. */
+int pc_debug_tonemap(pc_tracer *tr, const float *acc, uint32_t n, float sample_weight,
+                     float exposure, uint8_t *rgba_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLARIS_CUDA_H */
