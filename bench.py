@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the tracer hot path on B200 (driver contract).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, N > 1)
+
+N = 1  workload = BASELINE.json configs[1]: layered-material Cornell box, 1024x1024, 256 spp,
+       5 bounces, RR after 3.  One step = one frame: Trace + MergeOutput + SyncFramebuffer.
+N > 1  workload = configs[4]: the same scene at 3840x2160, rows split across the ranks by the
+       restated `perfect` block scheduler; one step = one 64-spp pass: every rank traces its row
+       block, the blocks are gathered to rank 0 over NCCL/NVLink and added, rank 0 tonemaps.
+Metric = Mrays/s over all bounces (closest-hit + occlusion rays, counted on the device).
+
+`value`   whole-job Mrays/s, scene resident in HBM before the timed region.
+`e2e`     same metric through the public Tracer API with HOST scene buffers: every step uploads the
+          scene + camera from host memory, traces, and reads the RGBA8 frame back to the host.
+`roofline`  dominant kernel's algorithmic bytes per launch / its CUDA-event time per launch (a second
+          pass of the same workload in PC_OPT_KERNEL_TIMERS mode, device counters on), against the
+          measured HBM copy bandwidth of MEASURED_PEAKS.json.
+`cpu_baseline`  the CPU implementation (oracle/_ref = the reference's own kernels compiled for the
+          CPU when present, else the oracle port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NUM_BOUNCES, MIN_RR, EXPOSURE = 5, 3, 1.2
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes per launch of each kernel class: SURVEY §8(d) per-unit figures x the units the
+# launch processed (device counters).  DESIGN.md §Roofline restates this table.
+def algorithmic_bytes(st, frame_px, nb):
+    q, o = st["query_rays"], st["occlusion_rays"]
+    trav = 64 * st["nodes_tested"] + 80 * st["instances_entered"] + 48 * st["tris_tested"]
+    # split traversal payload between the kernels by their ray share (counters are per trace call)
+    share_q = q / max(1, q + o)
+    prim_rays = frame_px * st["_spp"]
+    ind_rays = q - prim_rays
+    by = {
+        "k_primary": 64 * prim_rays + 36 * prim_rays + trav * share_q * (prim_rays / max(1, q)),
+        "k_query": (32 + 4 + 32) * ind_rays + trav * share_q * (ind_rays / max(1, q)),
+        "k_occlusion": 32 * o + trav * (1 - share_q) + (4 + 16 + 32) * st["unoccluded"],
+        "k_shade": (36 * q + (64 + 124 + 64 + 80 + 120 + 32) * st["shaded_hits"] + 48 * st["occlusion_emitted"]
+                    + 32 * st["indirect_emitted"] + 96 * st["missed_query_rays"] * (1 if st["_background"] else 0)),
+    }
+    return by
+
+
+# ------------------------------------------------------------------------------------------------
+def build_scene(name, w, h):
+    from polaris_b200 import scenes
+
+    t0 = time.time()
+    sc, _, _, _ = scenes.build(name, w, h)
+    log(f"[bench] scene {name} {w}x{h}: {sc.num_triangles} triangles, {len(sc.bvh_nodes)} BVH nodes, "
+        f"{sc.nbytes() / 1e6:.2f} MB, compiled in {time.time() - t0:.1f}s")
+    return sc
+
+
+def cpu_trace_sample(sc, w, h, spp, config_number, rows=None):
+    """Bounded CPU run of the same workload: returns (Mrays/s, cores, kind, seconds, rays)."""
+    from polaris_b200 import tracer as T
+
+    kind = "port"
+    tr = None
+    try:
+        from oracle import ref_binding
+
+        if ref_binding.available():
+            tr = ref_binding.RefTracer()
+            kind = "reference"
+    except Exception as e:  # pragma: no cover
+        log(f"[bench] oracle/_ref unavailable ({e}); using the oracle port")
+    if tr is None:
+        from oracle.binding import OracleTracer
+
+        tr = OracleTracer()
+    tr.init()
+    tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
+    tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+    tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+    bh = rows or h
+    req = T.make_block_request(w, h, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+    seeds = T.splitmix_seeds(config_number, spp * (1 + NUM_BOUNCES))
+    t0 = time.perf_counter()
+    tr.trace(req, seeds)
+    tr.merge_output(tr, req)
+    tr.sync_framebuffer(T.make_block_request(w, h, spp=spp, exposure=EXPOSURE))
+    dt = time.perf_counter() - t0
+    d = tr.stats().device
+    rays = d["query_rays"] + d["occlusion_rays"]
+    tr.close()
+    return rays / dt / 1e6, (os.cpu_count() or 1), kind, dt, rays
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.gpus
+    if n == 1:
+        name, w, h, spp_full, cfgno = "c2_cornell", 1024, 1024, 256, 2
+    else:
+        name, w, h, spp_full, cfgno = "c5_cornell_4k", 3840, 2160, 1024, 5
+    sc = build_scene(name, w, h)
+    # bounded sample per step so that warmup+steps finish within a few minutes
+    spp = 2 if n == 1 else 1
+    rows = h if n == 1 else 540
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, cores, kind, dt, rays = cpu_trace_sample(sc, w, h, spp, cfgno, rows)
+        log(f"[bench:reference] step {i}: {v:.2f} Mrays/s ({dt:.2f}s, {rays} rays, kind={kind}, cores={cores})")
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    value = float(np.mean(vals))
+    sample = f"{w}x{rows} rows of the {w}x{h} frame, {spp} spp of {spp_full} per step"
+    line = {
+        "impl": "reference", "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": n,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n, w, h, spp_full),
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(n, w, h, spp):
+    if n == 1:
+        wl = "configs[1]: synthetic Cornell box, layered diffuse/conductor/dielectric materials, 1024x1024, 256 spp"
+    else:
+        wl = f"configs[4]: 3840x2160 layered Cornell box, 1024 spp in 64-spp passes, rows split over {n} GPUs by the perfect scheduler"
+    return {"workload": wl, "frame": [w, h], "spp": spp, "num_bounces": NUM_BOUNCES, "min_bounces_for_rr": MIN_RR,
+            "l2": "per-step ray/path state (220 B/px x frame, re-written every bounce) exceeds the 126 MB L2; scene data is L2 resident by design"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_cuda_single(args):
+    import torch  # device plumbing only (event/synchronize helpers are not needed; kept for parity with N>1)
+
+    from polaris_b200 import _lib
+    from polaris_b200 import tracer as T
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    w, h, spp, cfgno = 1024, 1024, args.spp or 256, 2
+    sc = build_scene("c2_cornell", w, h)
+    seeds = T.splitmix_seeds(cfgno, spp * (1 + NUM_BOUNCES))
+    tr = T.CudaTracer("cuda:0", 0)
+    tr.init()
+    tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
+    tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+    tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+
+    def frame(e2e=False):
+        if e2e:  # host scene buffers -> device, every step
+            tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+            tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+        req = T.make_block_request(w, h, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+        tr.trace(req, seeds)
+        tr.merge_output(tr, req)
+        tr.sync_framebuffer(T.make_block_request(w, h, spp=spp, exposure=EXPOSURE), want_pixels=e2e)
+        d = tr.stats().device
+        return d["query_rays"] + d["occlusion_rays"], d["kernel_launches"] + 2, d["device_time_ns"]
+
+    for i in range(args.warmup):
+        t0 = time.perf_counter()
+        rays, _, _ = frame()
+        log(f"[bench] warmup {i}: {rays / (time.perf_counter() - t0) / 1e6:.1f} Mrays/s")
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tot_rays = tot_launch = tot_dev_ns = 0
+    for _ in range(args.steps):
+        rays, launches, dev_ns = frame()
+        tot_rays += rays
+        tot_launch += launches
+        tot_dev_ns += dev_ns
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clk = clocks.stop()
+    value = tot_rays / dt / 1e6
+    log(f"[bench] timed: {args.steps} steps in {dt:.3f}s -> {value:.1f} Mrays/s ({tot_dev_ns / 1e9:.3f}s device time in pc_trace)")
+
+    # ---- e2e: through the public API with host buffers, H2D scene + D2H frame inside the timed region
+    frame(e2e=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e_rays = 0
+    for _ in range(args.steps):
+        r, _, _ = frame(e2e=True)
+        e_rays += r
+    torch.cuda.synchronize()
+    e_dt = time.perf_counter() - t0
+    h2d = sc.nbytes() + seeds.nbytes + 76
+    d2h = w * h * 4
+
+    # ---- roofline pass: same workload, per-kernel CUDA events + device counters
+    tr.set_option(_lib.OPT_KERNEL_TIMERS, 1)
+    tr.set_option(_lib.OPT_COUNTERS, 1)
+    prof_spp = min(spp, 32)
+    req = T.make_block_request(w, h, spp=prof_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+    tr.trace(req, seeds[: prof_spp * (1 + NUM_BOUNCES)])
+    st = tr.stats().device
+    st["_spp"], st["_background"] = prof_spp, sc.scene_diffuse_mat_index != -1
+    by = algorithmic_bytes(st, w * h, NUM_BOUNCES)
+    times = {n: st["kernel_time_ns"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
+    counts = {n: st["kernel_count"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
+    total_ns = sum(times.values())
+    dom = max(("k_primary", "k_shade", "k_occlusion", "k_query"), key=lambda k: times[k])
+    peak, peak_src = measured_hbm_peak()
+    kern = {}
+    for k in ("k_primary", "k_shade", "k_occlusion", "k_query"):
+        if counts[k]:
+            kern[k] = {"launches": counts[k], "avg_us": times[k] / counts[k] / 1e3, "share": times[k] / max(1, total_ns),
+                       "alg_GBps": by[k] / max(1, times[k])}
+    log("[bench] kernel classes: " + json.dumps(kern))
+    achieved = by[dom] / max(1, times[dom])  # bytes per ns == GB/s
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / max(1, counts[dom]),
+                "avg_launch_us": times[dom] / max(1, counts[dom]) / 1e3, "kernels": kern,
+                "rays_per_path": (st["query_rays"] + st["occlusion_rays"]) / (w * h * prof_spp),
+                "nodes_per_ray": st["nodes_tested"] / max(1, st["query_rays"] + st["occlusion_rays"]),
+                "tris_per_ray": st["tris_tested"] / max(1, st["query_rays"] + st["occlusion_rays"])}
+    tr.close()
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if not args.no_cpu:
+        v, cores, kind, cdt, crays = cpu_trace_sample(sc, w, h, args.cpu_spp, cfgno)
+        cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind,
+               "sample": f"{w}x{h}, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
+        log(f"[bench] cpu baseline ({kind}, {cores} cores): {v:.2f} Mrays/s")
+
+    line = {
+        "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp),
+        "spp_mpix_per_s": w * h * spp * args.steps / dt / 1e6, "gpu_launches": int(tot_launch), "clocks": clk,
+        "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+class _DevPtr:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_cuda_multi(args):
+    import torch
+    import torch.distributed as dist
+
+    from polaris_b200 import tracer as T
+    from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h, pass_spp, cfgno = 3840, 2160, args.spp or 64, 5
+    sc = build_scene("c5_cornell_4k", w, h) if rank == 0 else None
+    objs = [sc]
+    dist.broadcast_object_list(objs, src=0)  # every GPU holds the full scene (default.go:70-72)
+    sc = objs[0]
+    tr = T.CudaTracer(f"cuda:{local}", local)
+    tr.init()
+    tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
+    tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+    tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+    sched = PerfectScheduler()
+    speeds = [StaticSpeed(tr.speed()) for _ in range(world)]
+    seeds = T.splitmix_seeds(cfgno + 100 * rank, pass_spp * (1 + NUM_BOUNCES))
+    recv = torch.empty(w * h * 4, dtype=torch.float32, device="cuda") if rank == 0 else None
+    acc_samples = 0
+
+    def step(e2e=False):
+        nonlocal acc_samples
+        rows = sched.schedule(speeds, h)  # identical on every rank: fed by all-gathered timings below
+        by = int(sum(rows[:rank]))
+        req = T.make_block_request(w, h, block_y=by, block_h=int(rows[rank]), spp=pass_spp, num_bounces=NUM_BOUNCES,
+                                   min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=acc_samples)
+        if e2e:
+            tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+            tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+        t0 = time.perf_counter()
+        tr.trace(req, seeds)
+        t_trace = time.perf_counter() - t0
+        d = tr.stats().device
+        # exchange step: block rows -> rank 0 over NCCL (NVLink), added into the frame accumulator
+        ptr, nbytes = tr.trace_rows(req)
+        mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
+        if rank == 0:
+            tr.merge_output(tr, req)
+            reqs = []
+            off = 0
+            for r in range(1, world):
+                n = w * int(rows[r]) * 4
+                reqs.append((r, off, n, dist.irecv(recv[off:off + n], src=r)))
+                off += n
+            for r, off, n, work in reqs:
+                work.wait()
+                torch.cuda.synchronize()
+                rr = T.make_block_request(w, h, block_y=int(sum(rows[:r])), block_h=int(rows[r]), spp=pass_spp,
+                                          accumulated_samples=acc_samples + pass_spp)
+                tr.merge_rows(recv[off:off + n].data_ptr(), True, rr)
+            tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc_samples), want_pixels=e2e)
+        else:
+            dist.send(mine, dst=0)
+        # feedback for the perfect scheduler (scheduler.go:50-80): rows and render time of every tracer
+        t = torch.tensor([float(rows[rank]), t_trace, float(d["query_rays"] + d["occlusion_rays"]), float(d["kernel_launches"])],
+                         dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        for r in range(world):
+            speeds[r].set_stats(int(allt[r][0].item()), float(allt[r][1].item()))
+        acc_samples += pass_spp
+        return sum(float(x[2].item()) for x in allt), sum(float(x[3].item()) for x in allt)
+
+    for i in range(args.warmup):
+        step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rays = launches = 0.0
+    for _ in range(args.steps):
+        r, l = step()
+        rays += r
+        launches += l
+    dist.barrier()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt.item())
+    clk = clocks.stop() if rank == 0 else None
+    # e2e
+    step(e2e=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e_rays = 0.0
+    for _ in range(args.steps):
+        r, _ = step(e2e=True)
+        e_rays += r
+    dist.barrier()
+    torch.cuda.synchronize()
+    e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
+    e_dt = float(e_dt.item())
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s (all bounces)", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, w, h, 1024),
+            "spp_mpix_per_s": w * h * pass_spp * args.steps / dt / 1e6, "gpu_launches": int(launches) + 2 * args.steps * world,
+            "clocks": clk, "rows_last_step": [int(s.block_h) for s in speeds],
+            "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s",
+                    "h2d_bytes_per_step": int((sc.nbytes() + seeds.nbytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
+            "roofline": None, "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    tr.close()
+    dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--spp", type=int, default=0, help="override samples per step (debugging only; invalidates the config)")
+    ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_cuda_multi(args)
+    if args.gpus > 1:
+        log("[bench] --gpus > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        return 2
+    return run_cuda_single(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -83,7 +83,15 @@ typedef struct pc_stats {
     uint64_t indirect_emitted;
     uint64_t unoccluded;
     uint64_t missed_query_rays;
+    /* valid only when PC_OPT_KERNEL_TIMERS is on: CUDA-event time and launch count per kernel
+     * class of the last pc_trace, see pc_kernel_class */
+    uint64_t kernel_time_ns[8];
+    uint64_t kernel_count[8];
 } pc_stats;
+
+typedef enum pc_kernel_class {
+    PC_K_BEGIN_SAMPLE = 0, PC_K_PRIMARY = 1, PC_K_SHADE = 2, PC_K_OCCLUSION = 3, PC_K_QUERY = 4
+} pc_kernel_class;
 
 /* scene.Scene flat buffers, reference asset/scene/optimized_scene.go:167-190, in the
  * order tracer/opencl/buffers.go:180-191 uploads them. Byte sizes, not counts. */
@@ -123,8 +131,10 @@ typedef enum pc_option {
     PC_OPT_REFERENCE_ORDER = 2, /* 1: left-first traversal without closest-hit culling,
                                    i.e. literally intersect.cl:184-347; default 0         */
     PC_OPT_USE_GRAPH = 3,       /* 1 (default): replay one CUDA graph per sample          */
-    PC_OPT_FIX_Q4 = 4           /* 1 (default): emissive hits accumulate at pixelIndex;
+    PC_OPT_FIX_Q4 = 4,          /* 1 (default): emissive hits accumulate at pixelIndex;
                                    0: at the ray's path index like pt_integrator.cl:106   */
+    PC_OPT_KERNEL_TIMERS = 5    /* 1: direct launches bracketed by CUDA events on the handle's
+                                   stream, per-class times in pc_stats (measurement mode)   */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */

@@ -35,10 +35,14 @@ class Stats(ctypes.Structure):
     _fields_ = [("block_w", u32), ("block_h", u32), ("update_time_ns", u64), ("render_time_ns", u64),
                 ("device_time_ns", u64), ("query_rays", u64), ("occlusion_rays", u64), ("kernel_launches", u64),
                 ("nodes_tested", u64), ("tris_tested", u64), ("instances_entered", u64), ("shaded_hits", u64),
-                ("occlusion_emitted", u64), ("indirect_emitted", u64), ("unoccluded", u64), ("missed_query_rays", u64)]
+                ("occlusion_emitted", u64), ("indirect_emitted", u64), ("unoccluded", u64), ("missed_query_rays", u64),
+                ("kernel_time_ns", u64 * 8), ("kernel_count", u64 * 8)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["kernel_time_ns"] = list(d["kernel_time_ns"])
+        d["kernel_count"] = list(d["kernel_count"])
+        return d
 
 
 class SceneView(ctypes.Structure):
@@ -61,7 +65,9 @@ assert ctypes.sizeof(BlockRequest) == 48
 BUF_RAYS0, BUF_RAYS1, BUF_RAYS2, BUF_PATHS, BUF_HIT_FLAGS, BUF_INTERSECTIONS = 0, 1, 2, 3, 4, 5
 BUF_EMISSIVE_SAMPLES, BUF_TRACE_ACCUMULATOR, BUF_FRAME_ACCUMULATOR, BUF_FRAME_BUFFER, BUF_RAY_COUNTERS = 6, 7, 8, 9, 10
 # pc_option
-OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4 = 0, 1, 2, 3, 4
+OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS = 0, 1, 2, 3, 4, 5
+K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY = 0, 1, 2, 3, 4
+KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query"]
 # pc_status
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_ALLOC, ERR_COPY_TO_DEVICE, ERR_COPY_TO_HOST, ERR_KERNEL = 1, 2, 3, 4, 5, 6

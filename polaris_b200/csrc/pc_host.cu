@@ -1,0 +1,789 @@
+// pc_host.cu -- libpolaris_cuda.so: the C ABI of include/polaris_cuda.h over the CUDA kernels.
+//
+// This is the host half of the reference's tracer/opencl package re-expressed for CUDA:
+//   tracer.go     (state machine, Trace / MergeOutput / SyncFramebuffer)   -> pc_trace & co.
+//   pipeline.go   (MonteCarloIntegrator bounce loop)                       -> record_sample()
+//   resources.go  (one method per kernel launch, argument wiring)          -> the launch_* helpers
+//   buffers.go    (bufferSet: Resize / UploadSceneData)                    -> pc_resize / pc_upload_scene
+//   device/*.go   (OpenCL wrapper)                                         -> CUDA runtime, one stream per handle
+// Differences that matter: no host synchronisation inside a sample (ray counts stay on the device),
+// one CUDA graph replayed per sample, seeds are an explicit input.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/polaris_cuda.h"
+#include "pc_kernels.cuh"
+#include "pc_layout.hpp"
+
+using namespace pc;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t alloc(size_t n) {
+        release();
+        if (n == 0) n = 16;  // keep pointers non-null for empty tables
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+
+struct GraphKey {
+    uint32_t frameW = 0, blockY = 0, blockH = 0, nb = 0, rr = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0;
+    uint64_t sceneEpoch = 0, cameraEpoch = 0;
+    bool operator==(const GraphKey &o) const {
+        return frameW == o.frameW && blockY == o.blockY && blockH == o.blockH && nb == o.nb && rr == o.rr &&
+               counters == o.counters && packets == o.packets && reforder == o.reforder && fixq4 == o.fixq4 &&
+               sceneEpoch == o.sceneEpoch && cameraEpoch == o.cameraEpoch;
+    }
+};
+
+}  // namespace
+
+struct pc_tracer {
+    std::mutex mu;
+    int device = 0;
+    std::string id, err;
+    cudaDeviceProp prop{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool dead = false;
+    // scene
+    DevBuf bvh, inst, mats, texData, texMeta, verts, normals, uvs, matIdx, emissives, node64, tri48, inst80;
+    DScene sc{};
+    bool hasScene = false;
+    int stackNeed = 0;
+    uint64_t sceneEpoch = 0, cameraEpoch = 0;
+    // frame
+    uint32_t W = 0, H = 0;
+    DevBuf rays[3], paths, hitFlags, hits, emSamples, traceAcc, frameAcc, frameBuf, ctl, status, seedsDev, scratch;
+    FrameBufs fb{};
+    size_t statusStride = 0;  // words per bounce
+    CameraParams cam{};
+    bool hasCamera = false;
+    // options
+    int optCounters = 0, optPackets = 1, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0;
+    std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
+    std::vector<int> timerClass;
+    // graph cache
+    cudaGraphExec_t graphExec = nullptr;
+    GraphKey graphKey;
+    uint64_t launchesPerSample = 0;
+    // frame state (DESIGN.md "frame accumulator reset")
+    bool frameOpen = false, frameOpenByMerge = false;
+    pc_stats stats{};
+    uint64_t seedState = 0x501A2150ull;
+    int persistentGrid = 0;
+};
+
+namespace {
+
+int fail(pc_tracer *tr, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (tr) tr->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(tr, code, call)                                                                     \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            if ((code) == PC_ERR_KERNEL) (tr)->dead = true;                                    \
+            return fail((tr), (code), "%s: %s", #call, cudaGetErrorString(e_));                \
+        }                                                                                      \
+    } while (0)
+
+int enter(pc_tracer *tr) {
+    if (!tr) return PC_ERR_INVALID_ARGUMENT;
+    if (tr->dead) return fail(tr, PC_ERR_KERNEL, "tracer is dead after a sticky CUDA error: %s", tr->err.c_str());
+    cudaError_t e = cudaSetDevice(tr->device);
+    if (e != cudaSuccess) return fail(tr, PC_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", tr->device, cudaGetErrorString(e));
+    return 0;
+}
+
+int grid_for(size_t n, int block, int cap) {
+    size_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (size_t)cap) g = cap;
+    return (int)g;
+}
+
+uint32_t next_seed(uint64_t &s) {  // splitmix64
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)z;
+}
+
+void drop_graph(pc_tracer *tr) {
+    if (tr->graphExec) cudaGraphExecDestroy(tr->graphExec);
+    tr->graphExec = nullptr;
+}
+
+// ---- one sample of Tracer.Trace: PrimaryRayGenerator + MonteCarloIntegrator (pipeline.go:94-213)
+// enqueued on the handle's stream; every launch below is also a node of the per-sample graph.
+// PC_OPT_KERNEL_TIMERS: bracket a launch with two events on the launching stream
+struct LaunchTimer {
+    pc_tracer *tr;
+    size_t slot = 0;
+    LaunchTimer(pc_tracer *t, int cls) : tr(t) {
+        if (!tr->optTimers) return;
+        slot = tr->timerClass.size();
+        while (tr->timerEvents.size() < 2 * (slot + 1)) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            tr->timerEvents.push_back(e);
+        }
+        tr->timerClass.push_back(cls);
+        cudaEventRecord(tr->timerEvents[2 * slot], tr->stream);
+    }
+    ~LaunchTimer() {
+        if (tr->optTimers) cudaEventRecord(tr->timerEvents[2 * slot + 1], tr->stream);
+    }
+};
+
+template <bool COUNT>
+void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launches) {
+    cudaStream_t s = tr->stream;
+    TraceCtl *ctl = (TraceCtl *)tr->ctl.p;
+    const uint32_t *seeds = (const uint32_t *)tr->seedsDev.p;
+    unsigned long long *status = (unsigned long long *)tr->status.p;
+    const uint32_t nb = req.num_bounces, perSample = 1 + nb;
+    const uint32_t N = req.frame_w * req.block_h;
+    const int pg = tr->persistentGrid;
+    const int shadeGrid = (int)((N + SHADE_BLOCK - 1) / SHADE_BLOCK);
+    uint64_t L = 0;
+    size_t statusWords = tr->statusStride * nb;
+    {
+        LaunchTimer lt(tr, PC_K_BEGIN_SAMPLE);
+        k_begin_sample<<<grid_for(statusWords, 256, 1024), 256, 0, s>>>(ctl, status, statusWords);
+    }
+    L++;
+    int slot = 0;
+    // generatePrimaryRays + RayPacketIntersectionQuery / RayIntersectionQuery (pipeline.go:107-111)
+    {
+    LaunchTimer lt(tr, PC_K_PRIMARY);
+    if (tr->optRefOrder)
+        k_primary<2, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+    else if (tr->optPackets)
+        k_primary<1, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+    else
+        k_primary<0, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+    }
+    L++;
+    slot++;
+    int a = 0;
+    for (uint32_t bounce = 0; bounce < nb; bounce++) {
+        // ShadePrimaryRayMisses / ShadeIndirectRayMisses + ShadeHits (pipeline.go:134-146)
+        {
+            LaunchTimer lt(tr, PC_K_SHADE);
+            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
+                                                            perSample, bounce, req.min_bounces_for_rr, a, tr->optFixQ4);
+        }
+        L++;
+        // RayIntersectionTest(2) + AccumulateEmissiveSamples(2) (pipeline.go:160-165)
+        {
+        LaunchTimer lt(tr, PC_K_OCCLUSION);
+        if (tr->optRefOrder)
+            k_occlusion<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[2], tr->fb.paths, tr->fb.emissiveSamples, tr->fb.traceAcc, nullptr, ctl, slot);
+        else
+            k_occlusion<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[2], tr->fb.paths, tr->fb.emissiveSamples, tr->fb.traceAcc, nullptr, ctl, slot);
+        }
+        L++;
+        slot++;
+        if (bounce + 1 < nb) {  // pipeline.go:203-209
+            a = 1 - a;
+            LaunchTimer lt(tr, PC_K_QUERY);
+            if (tr->optRefOrder)
+                k_query<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[a], tr->fb.hitFlags, tr->fb.hits, ctl, a, slot);
+            else
+                k_query<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[a], tr->fb.hitFlags, tr->fb.hits, ctl, a, slot);
+            L++;
+            slot++;
+        }
+    }
+    *launches = L;
+}
+
+void record_sample(pc_tracer *tr, const pc_block_request &req, uint64_t *launches) {
+    if (tr->optCounters) record_sample_t<true>(tr, req, launches);
+    else record_sample_t<false>(tr, req, launches);
+}
+
+int upload(pc_tracer *tr, DevBuf &b, const void *src, size_t bytes) {
+    CU(tr, PC_ERR_ALLOC, b.alloc(bytes));
+    if (bytes) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, tr->stream));
+    return 0;
+}
+
+int clear_acc(pc_tracer *tr, DevBuf &b) {
+    size_t n = (size_t)tr->W * tr->H;
+    k_clear<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, tr->stream>>>((float4 *)b.p, n);
+    CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+    return 0;
+}
+
+bool first_pass(const pc_block_request *r) { return r->accumulated_samples <= r->samples_per_pixel; }
+
+int open_frame_for_merge(pc_tracer *dst, const pc_block_request *req) {
+    // The reference clears the frame accumulator inside each tracer's own Trace, racing with
+    // other workers' MergeOutput into the primary.  Here the first first-pass merge
+    // or the tracer's own first-pass Trace -- whichever arrives first -- does the one clear.
+    if (!dst->frameOpen && first_pass(req)) {
+        int rc = clear_acc(dst, dst->frameAcc);
+        if (rc) return rc;
+        dst->frameOpen = true;
+        dst->frameOpenByMerge = true;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pc_abi_version(void) { return PC_ABI_VERSION; }
+
+int pc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pc_device_info(int ordinal, char *name, size_t cap, uint32_t *sm_count, uint32_t *clock_mhz, uint32_t *speed) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, ordinal) != cudaSuccess) return PC_ERR_NO_DEVICE;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ordinal);
+    if (name && cap) snprintf(name, cap, "%s", p.name);
+    uint32_t mhz = (uint32_t)(khz / 1000);
+    if (sm_count) *sm_count = (uint32_t)p.multiProcessorCount;
+    if (clock_mhz) *clock_mhz = mhz;
+    if (speed) *speed = (uint32_t)p.multiProcessorCount * mhz / 1000u;  // device.go:209-222
+    return 0;
+}
+
+int pc_create(int ordinal, const char *id, pc_tracer **out) {
+    if (!out) return PC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = pc_device_count();
+    if (ordinal < 0 || ordinal >= n) return fail(nullptr, PC_ERR_NO_DEVICE, "CUDA device %d not available (%d devices)", ordinal, n);
+    auto *tr = new pc_tracer();
+    tr->device = ordinal;
+    tr->id = id ? id : "cuda";
+    cudaError_t e = cudaSetDevice(ordinal);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&tr->prop, ordinal);
+    if (e == cudaSuccess && tr->prop.major < 10) {
+        fail(nullptr, PC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", ordinal, tr->prop.major, tr->prop.minor);
+        delete tr;
+        return PC_ERR_NO_DEVICE;
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&tr->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&tr->evStart);
+    if (e == cudaSuccess) e = cudaEventCreate(&tr->evStop);
+    if (e == cudaSuccess) e = tr->ctl.alloc(sizeof(TraceCtl));
+    if (e == cudaSuccess) e = cudaMemsetAsync(tr->ctl.p, 0, sizeof(TraceCtl), tr->stream);
+    if (e != cudaSuccess) {
+        fail(nullptr, PC_ERR_NO_DEVICE, "pc_create(%d): %s", ordinal, cudaGetErrorString(e));
+        delete tr;
+        return PC_ERR_NO_DEVICE;
+    }
+    // persistent grid: every SM full of traversal blocks (multiple of the SM count)
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_query<false, false>, TRAV_BLOCK, 0);
+    if (perSM < 1) perSM = 1;
+    if (perSM > 8) perSM = 8;
+    tr->persistentGrid = tr->prop.multiProcessorCount * perSM;
+    tr->sc.sceneDiffuseMat = -1;
+    *out = tr;
+    return 0;
+}
+
+void pc_destroy(pc_tracer *tr) {
+    if (!tr) return;
+    {
+        std::lock_guard<std::mutex> g(tr->mu);
+        cudaSetDevice(tr->device);
+        if (tr->stream) cudaStreamSynchronize(tr->stream);
+        drop_graph(tr);
+        DevBuf *all[] = {&tr->bvh, &tr->inst, &tr->mats, &tr->texData, &tr->texMeta, &tr->verts, &tr->normals, &tr->uvs,
+                         &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->rays[0], &tr->rays[1],
+                         &tr->rays[2], &tr->paths, &tr->hitFlags, &tr->hits, &tr->emSamples, &tr->traceAcc, &tr->frameAcc,
+                         &tr->frameBuf, &tr->ctl, &tr->status, &tr->seedsDev, &tr->scratch};
+        for (DevBuf *b : all) b->release();
+        for (cudaEvent_t e : tr->timerEvents) cudaEventDestroy(e);
+        if (tr->evStart) cudaEventDestroy(tr->evStart);
+        if (tr->evStop) cudaEventDestroy(tr->evStop);
+        if (tr->stream) cudaStreamDestroy(tr->stream);
+    }
+    delete tr;
+}
+
+const char *pc_id(const pc_tracer *tr) { return tr ? tr->id.c_str() : ""; }
+uint32_t pc_flags(const pc_tracer *) { return 1u; /* tracer.Local */ }
+uint32_t pc_speed(const pc_tracer *tr) {
+    if (!tr) return 0;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, tr->device);
+    return (uint32_t)tr->prop.multiProcessorCount * (uint32_t)(khz / 1000) / 1000u;
+}
+const char *pc_last_error(const pc_tracer *tr) {
+    if (!tr) return g_create_error.empty() ? nullptr : g_create_error.c_str();
+    return tr->err.empty() ? nullptr : tr->err.c_str();
+}
+
+int pc_set_option(pc_tracer *tr, int option, int value) {
+    if (!tr) return PC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(tr->mu);
+    switch (option) {
+        case PC_OPT_COUNTERS: tr->optCounters = value != 0; break;
+        case PC_OPT_PRIMARY_PACKETS: tr->optPackets = value != 0; break;
+        case PC_OPT_REFERENCE_ORDER: tr->optRefOrder = value != 0; break;
+        case PC_OPT_USE_GRAPH: tr->optGraph = value != 0; break;
+        case PC_OPT_FIX_Q4: tr->optFixQ4 = value != 0; break;
+        case PC_OPT_KERNEL_TIMERS: tr->optTimers = value != 0; break;
+        default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+    }
+    return 0;
+}
+
+// bufferSet.Resize (buffers.go:127-175).  Ray / path state is frame sized like the reference's.
+int pc_resize(pc_tracer *tr, uint32_t w, uint32_t h) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (w == 0 || h == 0 || (uint64_t)w * h >= (1ull << 24)) {
+        // path indices travel as floats in ray.dir.w and are exact only below 2^24
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "frame %ux%u unsupported: needs 0 < pixels < 2^24", w, h);
+    }
+    if (w == tr->W && h == tr->H) return 0;
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    drop_graph(tr);
+    const size_t px = (size_t)w * h;
+    for (auto &r : tr->rays) CU(tr, PC_ERR_ALLOC, r.alloc(px * 32));
+    CU(tr, PC_ERR_ALLOC, tr->paths.alloc(px * 32));
+    CU(tr, PC_ERR_ALLOC, tr->hitFlags.alloc(px * 4));
+    CU(tr, PC_ERR_ALLOC, tr->hits.alloc(px * 32));
+    CU(tr, PC_ERR_ALLOC, tr->emSamples.alloc(px * 16));
+    CU(tr, PC_ERR_ALLOC, tr->traceAcc.alloc(px * 16));
+    CU(tr, PC_ERR_ALLOC, tr->frameAcc.alloc(px * 16));
+    CU(tr, PC_ERR_ALLOC, tr->frameBuf.alloc(px * 4));
+    CU(tr, PC_ERR_ALLOC, tr->scratch.alloc(px * 32));
+    tr->statusStride = (px + SHADE_BLOCK - 1) / SHADE_BLOCK + 1;
+    CU(tr, PC_ERR_ALLOC, tr->status.alloc(tr->statusStride * MAX_BOUNCES * 8));
+    tr->W = w;
+    tr->H = h;
+    for (int i = 0; i < 3; i++) tr->fb.rays[i] = (Ray *)tr->rays[i].p;
+    tr->fb.paths = (PathRec *)tr->paths.p;
+    tr->fb.hitFlags = (uint32_t *)tr->hitFlags.p;
+    tr->fb.hits = (HitRec *)tr->hits.p;
+    tr->fb.emissiveSamples = (float4 *)tr->emSamples.p;
+    tr->fb.traceAcc = (float4 *)tr->traceAcc.p;
+    DevBuf *zero[] = {&tr->rays[0], &tr->rays[1], &tr->rays[2], &tr->paths, &tr->hitFlags, &tr->hits, &tr->emSamples,
+                      &tr->traceAcc, &tr->frameAcc, &tr->frameBuf, &tr->status};
+    for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
+    tr->frameOpen = tr->frameOpenByMerge = false;
+    return 0;
+}
+
+// bufferSet.UploadSceneData (buffers.go:177-201) + derived traversal layout (pc_layout.hpp)
+int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    if (!v) return fail(tr, PC_ERR_INVALID_ARGUMENT, "null scene view");
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (v->bvh_nodes_bytes < 32 || v->bvh_nodes_bytes % 32 || v->mesh_instances_bytes % 80 || v->material_nodes_bytes % 64 ||
+        v->texture_metadata_bytes % 16 || v->vertices_bytes % 48 || v->normals_bytes != v->vertices_bytes ||
+        v->uvs_bytes * 2 != v->vertices_bytes || v->material_indices_bytes * 12 != v->vertices_bytes || v->emissives_bytes % 80)
+        return fail(tr, PC_ERR_BAD_SCENE, "scene buffer sizes are inconsistent with the reference layouts");
+    const size_t nMat = v->material_nodes_bytes / 64;
+    if (v->scene_diffuse_mat_index >= (int64_t)nMat) return fail(tr, PC_ERR_BAD_SCENE, "scene diffuse material index out of range");
+    pc_layout::Builder lb((const pc_layout::RefNode *)v->bvh_nodes, v->bvh_nodes_bytes / 32,
+                          (const pc_layout::RefInstance *)v->mesh_instances, v->mesh_instances_bytes / 80,
+                          (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16);
+    pc_layout::Layout L = lb.build();
+    if (!L.error.empty()) return fail(tr, PC_ERR_BAD_SCENE, "%s", L.error.c_str());
+    if (L.stack_need > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
+        return fail(tr, PC_ERR_STACK_DEPTH, "BVH needs a %d-entry traversal stack, the kernels have %d", L.stack_need, PC_STACK_SIZE);
+    {   // validate what the shading kernels index with
+        const uint32_t *mi = (const uint32_t *)v->material_indices;
+        for (size_t i = 0; i < v->material_indices_bytes / 4; i++)
+            if (mi[i] >= nMat) return fail(tr, PC_ERR_BAD_SCENE, "triangle %zu references material node %u of %zu", i, mi[i], nMat);
+    }
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    drop_graph(tr);
+    if ((rc = upload(tr, tr->bvh, v->bvh_nodes, v->bvh_nodes_bytes))) return rc;
+    if ((rc = upload(tr, tr->inst, v->mesh_instances, v->mesh_instances_bytes))) return rc;
+    if ((rc = upload(tr, tr->mats, v->material_nodes, v->material_nodes_bytes))) return rc;
+    if ((rc = upload(tr, tr->texData, v->texture_data, v->texture_data_bytes))) return rc;
+    if ((rc = upload(tr, tr->texMeta, v->texture_metadata, v->texture_metadata_bytes))) return rc;
+    if ((rc = upload(tr, tr->verts, v->vertices, v->vertices_bytes))) return rc;
+    if ((rc = upload(tr, tr->normals, v->normals, v->normals_bytes))) return rc;
+    if ((rc = upload(tr, tr->uvs, v->uvs, v->uvs_bytes))) return rc;
+    if ((rc = upload(tr, tr->matIdx, v->material_indices, v->material_indices_bytes))) return rc;
+    if ((rc = upload(tr, tr->emissives, v->emissives, v->emissives_bytes))) return rc;
+    if ((rc = upload(tr, tr->node64, L.node64.data(), L.node64.size() * 16))) return rc;
+    if ((rc = upload(tr, tr->tri48, L.tri48.data(), L.tri48.size() * 16))) return rc;
+    if ((rc = upload(tr, tr->inst80, L.inst80.data(), L.inst80.size() * 16))) return rc;
+    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaStreamSynchronize(tr->stream));  // host vectors die with this scope
+    DScene &s = tr->sc;
+    s.node64 = (const float4 *)tr->node64.p;
+    s.tri48 = (const float4 *)tr->tri48.p;
+    s.inst80 = (const float4 *)tr->inst80.p;
+    s.rootRef = L.root_ref;
+    s.bvhNodes = (const float4 *)tr->bvh.p;
+    s.meshInstances = (const float4 *)tr->inst.p;
+    s.vertices = (const float4 *)tr->verts.p;
+    s.normals = (const float4 *)tr->normals.p;
+    s.uvs = (const float2 *)tr->uvs.p;
+    s.matIndex = (const uint32_t *)tr->matIdx.p;
+    s.matNodes = (const float4 *)tr->mats.p;
+    s.emissives = (const float4 *)tr->emissives.p;
+    s.texMeta = (const uint4 *)tr->texMeta.p;
+    s.texData = (const uint8_t *)tr->texData.p;
+    s.numEmissives = (uint32_t)(v->emissives_bytes / 80);
+    s.sceneDiffuseMat = v->scene_diffuse_mat_index;
+    tr->stackNeed = L.stack_need;
+    tr->hasScene = true;
+    tr->sceneEpoch++;
+    return 0;
+}
+
+int pc_set_camera(pc_tracer *tr, const float eye[3], const float frustum[16]) {
+    if (!tr || !eye || !frustum) return PC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(tr->mu);
+    tr->cam.eye = make_float3(eye[0], eye[1], eye[2]);
+    memcpy(&tr->cam.frustrumTL, frustum, 64);
+    tr->hasCamera = true;
+    tr->cameraEpoch++;
+    return 0;
+}
+
+// Tracer.Trace (tracer.go:194-247)
+int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    if (!req) return fail(tr, PC_ERR_INVALID_ARGUMENT, "null block request");
+    std::lock_guard<std::mutex> g(tr->mu);
+    auto t0 = std::chrono::steady_clock::now();
+    if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");  // errors.go:21
+    if (tr->W == 0 || req->frame_w != tr->W || req->frame_h != tr->H)
+        return fail(tr, PC_ERR_NO_FRAME, "block request is for a %ux%u frame, buffers are %ux%u", req->frame_w, req->frame_h, tr->W, tr->H);
+    if (req->block_y + req->block_h > req->frame_h || req->block_h == 0 || req->block_w != req->frame_w || req->block_x != 0)
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "block must be full-width rows inside the frame");
+    if (req->num_bounces == 0 || req->num_bounces > MAX_BOUNCES)
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "num_bounces must be in [1, %d]", MAX_BOUNCES);
+    const uint32_t spp = req->samples_per_pixel, perSample = 1 + req->num_bounces;
+    const size_t need = (size_t)perSample * spp;
+    if (seeds && n_seeds < need) return fail(tr, PC_ERR_INVALID_ARGUMENT, "need %zu seeds, got %zu", need, n_seeds);
+    std::vector<uint32_t> own;
+    if (!seeds) {  // the reference draws from Go's global math/rand (tracer.go:222, pipeline.go:146)
+        own.resize(need);
+        for (auto &x : own) x = next_seed(tr->seedState);
+        seeds = own.data();
+    }
+    cudaStream_t s = tr->stream;
+    // pipeline.Reset -> ClearFrameAccumulator when the sample counter was reset (tracer.go:208-213)
+    if (req->accumulated_samples == 0 && !tr->frameOpenByMerge) {
+        if ((rc = clear_acc(tr, tr->frameAcc))) return rc;
+    }
+    if (req->accumulated_samples == 0) tr->frameOpen = true;
+    if ((rc = clear_acc(tr, tr->traceAcc))) return rc;  // ClearTraceAccumulator (tracer.go:215)
+    if (need * 4 > tr->seedsDev.bytes) CU(tr, PC_ERR_ALLOC, tr->seedsDev.alloc(need * 4 + 4096));
+    if (need) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->seedsDev.p, seeds, need * 4, cudaMemcpyHostToDevice, s));
+    // reset the persistent part of the control block, keep the three ray counters
+    CU(tr, PC_ERR_KERNEL, cudaMemsetAsync((char *)tr->ctl.p + offsetof(TraceCtl, nextSample), 0,
+                                          sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
+    uint64_t launches = 2;
+    uint64_t perSampleLaunches = 0;
+    CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStart, s));
+    if (spp > 0) {
+        tr->timerClass.clear();
+        if (tr->optGraph && !tr->optTimers) {
+            GraphKey key;
+            key.frameW = req->frame_w; key.blockY = req->block_y; key.blockH = req->block_h;
+            key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
+            key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
+            key.sceneEpoch = tr->sceneEpoch; key.cameraEpoch = tr->cameraEpoch;
+            if (!tr->graphExec || !(key == tr->graphKey)) {
+                drop_graph(tr);
+                cudaGraph_t graph = nullptr;
+                CU(tr, PC_ERR_KERNEL, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+                record_sample(tr, *req, &tr->launchesPerSample);
+                CU(tr, PC_ERR_KERNEL, cudaStreamEndCapture(s, &graph));
+                cudaError_t e = cudaGraphInstantiate(&tr->graphExec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) {
+                    tr->graphExec = nullptr;
+                    return fail(tr, PC_ERR_KERNEL, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+                }
+                tr->graphKey = key;
+            }
+            perSampleLaunches = tr->launchesPerSample;
+            for (uint32_t i = 0; i < spp; i++) CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
+        } else {
+            for (uint32_t i = 0; i < spp; i++) {
+                record_sample(tr, *req, &perSampleLaunches);
+                CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+            }
+        }
+    }
+    CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStop, s));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(s));
+    CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tr->evStart, tr->evStop);
+    TraceCtl hc;
+    CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(&hc, tr->ctl.p, sizeof(hc), cudaMemcpyDeviceToHost));
+    if (spp) req->seed = seeds[(size_t)perSample * (spp - 1)];  // the last camera seed (tracer.go:222)
+    req->accumulated_samples += spp;                             // tracer.go:240
+    pc_stats &st = tr->stats;
+    memset(&st, 0, sizeof(st));
+    st.block_w = req->block_w;
+    st.block_h = req->block_h;
+    st.device_time_ns = (uint64_t)((double)ms * 1e6);
+    st.query_rays = hc.stats[ST_QUERY_RAYS];
+    st.occlusion_rays = hc.stats[ST_OCCLUSION_RAYS];
+    st.kernel_launches = launches + perSampleLaunches * spp;
+    st.nodes_tested = hc.stats[ST_NODES];
+    st.tris_tested = hc.stats[ST_TRIS];
+    st.instances_entered = hc.stats[ST_INSTANCES];
+    st.shaded_hits = hc.stats[ST_SHADED];
+    st.occlusion_emitted = hc.stats[ST_OCC_EMITTED];
+    st.indirect_emitted = hc.stats[ST_IND_EMITTED];
+    st.unoccluded = hc.stats[ST_UNOCCLUDED];
+    st.missed_query_rays = hc.stats[ST_MISSED];
+    if (tr->optTimers) {
+        for (size_t k = 0; k < tr->timerClass.size(); k++) {
+            float kms = 0.f;
+            if (cudaEventElapsedTime(&kms, tr->timerEvents[2 * k], tr->timerEvents[2 * k + 1]) == cudaSuccess) {
+                st.kernel_time_ns[tr->timerClass[k]] += (uint64_t)((double)kms * 1e6);
+                st.kernel_count[tr->timerClass[k]]++;
+            }
+        }
+    }
+    st.render_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    if (stats) *stats = st;
+    return 0;
+}
+
+int pc_get_stats(pc_tracer *tr, pc_stats *stats) {
+    if (!tr || !stats) return PC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(tr->mu);
+    *stats = tr->stats;
+    return 0;
+}
+
+static int check_block(pc_tracer *tr, const pc_block_request *req) {
+    if (!req) return fail(tr, PC_ERR_INVALID_ARGUMENT, "null block request");
+    if (tr->W == 0 || req->frame_w != tr->W || req->frame_h != tr->H) return fail(tr, PC_ERR_NO_FRAME, "frame dimensions do not match");
+    if ((uint64_t)req->frame_w * req->block_y + (uint64_t)req->block_w * req->block_h > (uint64_t)tr->W * tr->H)
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "block outside the frame");
+    return 0;
+}
+
+// Tracer.MergeOutput -> aggregateAccumulator with global offset FrameW*BlockY (resources.go:108-124)
+int pc_merge_output(pc_tracer *dst, pc_tracer *src, const pc_block_request *req) {
+    if (!src) return fail(dst, PC_ERR_UNSUPPORTED_TRACER, "merge failed: unsupported tracer instance");
+    int rc = enter(dst);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(dst->mu);  // workers call this concurrently on the primary
+    if ((rc = check_block(dst, req))) return rc;
+    if (src->W != dst->W || src->H != dst->H) return fail(dst, PC_ERR_NO_FRAME, "source tracer has different frame dimensions");
+    if (src->device != dst->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dst->device, src->device);
+        if (!can) return fail(dst, PC_ERR_PEER_ACCESS, "device %d cannot access device %d", dst->device, src->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(dst, PC_ERR_PEER_ACCESS, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    if ((rc = open_frame_for_merge(dst, req))) return rc;
+    const size_t off = (size_t)req->frame_w * req->block_y, n = (size_t)req->block_w * req->block_h;
+    // src finished its Trace before the caller got here (pc_trace is synchronous), so its rows are
+    // complete; the add is ordered on dst's stream and completes at pc_sync_framebuffer.
+    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->stream>>>((float4 *)dst->frameAcc.p, (const float4 *)src->traceAcc.p, off, off, n);
+    CU(dst, PC_ERR_KERNEL, cudaGetLastError());
+    return 0;
+}
+
+int pc_merge_rows(pc_tracer *dst, const void *rows, int is_device, const pc_block_request *req) {
+    int rc = enter(dst);
+    if (rc) return rc;
+    if (!rows) return fail(dst, PC_ERR_INVALID_ARGUMENT, "null rows");
+    std::lock_guard<std::mutex> g(dst->mu);
+    if ((rc = check_block(dst, req))) return rc;
+    if ((rc = open_frame_for_merge(dst, req))) return rc;
+    const size_t off = (size_t)req->frame_w * req->block_y, n = (size_t)req->block_w * req->block_h;
+    const float4 *src = (const float4 *)rows;
+    if (!is_device) {
+        CU(dst, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(dst->scratch.p, rows, n * 16, cudaMemcpyHostToDevice, dst->stream));
+        src = (const float4 *)dst->scratch.p;
+    }
+    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->stream>>>((float4 *)dst->frameAcc.p, src, off, 0, n);
+    CU(dst, PC_ERR_KERNEL, cudaGetLastError());
+    if (!is_device) CU(dst, PC_ERR_KERNEL, cudaStreamSynchronize(dst->stream));  // scratch is reused
+    return 0;
+}
+
+int pc_trace_rows(pc_tracer *tr, const pc_block_request *req, void **device_ptr, uint64_t *bytes) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if ((rc = check_block(tr, req))) return rc;
+    if (device_ptr) *device_ptr = (char *)tr->traceAcc.p + (size_t)req->frame_w * req->block_y * 16;
+    if (bytes) *bytes = (uint64_t)req->block_w * req->block_h * 16;
+    return 0;
+}
+
+// Tracer.SyncFramebuffer (tracer.go:250-276) + TonemapSimpleReinhard (resources.go:344-360)
+int pc_sync_framebuffer(pc_tracer *tr, const pc_block_request *req, uint8_t *rgba_out) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
+    if ((rc = check_block(tr, req))) return rc;
+    const size_t n = (size_t)req->frame_w * req->block_h;
+    const float sampleWeight = 1.0f / (float)(req->accumulated_samples + req->samples_per_pixel);  // resources.go:347
+    k_tonemap<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, tr->stream>>>((const float4 *)tr->frameAcc.p, (uchar4 *)tr->frameBuf.p, n, sampleWeight, req->exposure);
+    CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+    if (rgba_out) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(rgba_out, tr->frameBuf.p, (size_t)tr->W * tr->H * 4, cudaMemcpyDeviceToHost, tr->stream));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    tr->frameOpen = tr->frameOpenByMerge = false;
+    return 0;
+}
+
+int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    const void *src = nullptr;
+    size_t have = 0;
+    switch (which) {
+        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: src = tr->rays[which].p; have = tr->rays[which].bytes; break;
+        case PC_BUF_PATHS: src = tr->paths.p; have = tr->paths.bytes; break;
+        case PC_BUF_HIT_FLAGS: src = tr->hitFlags.p; have = tr->hitFlags.bytes; break;
+        case PC_BUF_INTERSECTIONS: src = tr->hits.p; have = tr->hits.bytes; break;
+        case PC_BUF_EMISSIVE_SAMPLES: src = tr->emSamples.p; have = tr->emSamples.bytes; break;
+        case PC_BUF_TRACE_ACCUMULATOR: src = tr->traceAcc.p; have = tr->traceAcc.bytes; break;
+        case PC_BUF_FRAME_ACCUMULATOR: src = tr->frameAcc.p; have = tr->frameAcc.bytes; break;
+        case PC_BUF_FRAME_BUFFER: src = tr->frameBuf.p; have = tr->frameBuf.bytes; break;
+        case PC_BUF_RAY_COUNTERS: src = tr->ctl.p; have = 12; break;
+        default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown buffer %d", which);
+    }
+    if (!src || bytes > have) return fail(tr, PC_ERR_INVALID_ARGUMENT, "buffer %d holds %zu bytes, %llu requested", which, have, (unsigned long long)bytes);
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode, uint32_t *out_flags, void *out_hits) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
+    if ((size_t)n > (size_t)tr->W * tr->H) return fail(tr, PC_ERR_INVALID_ARGUMENT, "%u rays exceed the frame's ray buffer", n);
+    cudaStream_t s = tr->stream;
+    TraceCtl *ctl = (TraceCtl *)tr->ctl.p;
+    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->rays[0].p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl, 0, sizeof(TraceCtl), s));
+    int cnt[3] = {(int)n, 0, (int)n};
+    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl, cnt, 12, cudaMemcpyHostToDevice, s));
+    const int pg = tr->persistentGrid;
+    if (mode == 0) {
+        if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, 0, 0);
+        else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, 0, 0);
+    } else if (mode == 1) {
+        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.paths, tr->fb.emissiveSamples, nullptr, tr->fb.hitFlags, ctl, 0);
+        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.paths, tr->fb.emissiveSamples, nullptr, tr->fb.hitFlags, ctl, 0);
+    } else if (mode == 2) {
+        k_debug_packet<false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, n, 0);
+    } else {
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown intersect mode %d", mode);
+    }
+    CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+    if (out_flags) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_flags, tr->hitFlags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (out_hits && mode != 1) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_hits, tr->hits.p, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int pc_debug_bxdf(pc_tracer *tr, const void *in_records, uint32_t n, void *out_records) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
+    DevBuf in, out;
+    CU(tr, PC_ERR_ALLOC, in.alloc((size_t)n * sizeof(BxdfIn)));
+    CU(tr, PC_ERR_ALLOC, out.alloc((size_t)n * sizeof(BxdfOut)));
+    cudaMemcpyAsync(in.p, in_records, (size_t)n * sizeof(BxdfIn), cudaMemcpyHostToDevice, tr->stream);
+    k_debug_bxdf<<<grid_for(n, 128, 65535), 128, 0, tr->stream>>>(tr->sc, (const BxdfIn *)in.p, (BxdfOut *)out.p, n);
+    cudaMemcpyAsync(out_records, out.p, (size_t)n * sizeof(BxdfOut), cudaMemcpyDeviceToHost, tr->stream);
+    cudaError_t e = cudaStreamSynchronize(tr->stream);
+    in.release();
+    out.release();
+    if (e != cudaSuccess) { tr->dead = true; return fail(tr, PC_ERR_KERNEL, "k_debug_bxdf: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int pc_debug_rng(pc_tracer *tr, uint32_t *states_inout, uint32_t n, uint32_t draws, float *out) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    DevBuf st, o;
+    CU(tr, PC_ERR_ALLOC, st.alloc((size_t)n * 8));
+    CU(tr, PC_ERR_ALLOC, o.alloc((size_t)n * draws * 8));
+    cudaMemcpyAsync(st.p, states_inout, (size_t)n * 8, cudaMemcpyHostToDevice, tr->stream);
+    k_debug_rng<<<grid_for(n, 128, 65535), 128, 0, tr->stream>>>((uint2 *)st.p, n, draws, (float2 *)o.p);
+    cudaMemcpyAsync(states_inout, st.p, (size_t)n * 8, cudaMemcpyDeviceToHost, tr->stream);
+    cudaMemcpyAsync(out, o.p, (size_t)n * draws * 8, cudaMemcpyDeviceToHost, tr->stream);
+    cudaError_t e = cudaStreamSynchronize(tr->stream);
+    st.release();
+    o.release();
+    if (e != cudaSuccess) { tr->dead = true; return fail(tr, PC_ERR_KERNEL, "k_debug_rng: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int pc_debug_tonemap(pc_tracer *tr, const float *acc, uint32_t n, float sample_weight, float exposure, uint8_t *rgba_out) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    DevBuf a, o;
+    CU(tr, PC_ERR_ALLOC, a.alloc((size_t)n * 16));
+    CU(tr, PC_ERR_ALLOC, o.alloc((size_t)n * 4));
+    cudaMemcpyAsync(a.p, acc, (size_t)n * 16, cudaMemcpyHostToDevice, tr->stream);
+    k_tonemap<<<grid_for(n, 256, 65535), 256, 0, tr->stream>>>((const float4 *)a.p, (uchar4 *)o.p, n, sample_weight, exposure);
+    cudaMemcpyAsync(rgba_out, o.p, (size_t)n * 4, cudaMemcpyDeviceToHost, tr->stream);
+    cudaError_t e = cudaStreamSynchronize(tr->stream);
+    a.release();
+    o.release();
+    if (e != cudaSuccess) { tr->dead = true; return fail(tr, PC_ERR_KERNEL, "k_tonemap: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+}  // extern "C"

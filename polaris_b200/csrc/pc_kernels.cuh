@@ -1,0 +1,565 @@
+// pc_kernels.cuh -- the __global__ kernels of the CUDA tracer (sm_100a).
+//
+// Wavefront organisation, one kernel per stage of the reference's pipeline (pipeline.go:94-213),
+// fused where a stage only post-processes its predecessor's per-ray output:
+//
+//   k_begin_sample  picks the sample's seeds, zeroes the per-sample work-queue heads / tickets
+//   k_primary       generatePrimaryRays (camera.cl) + closest-hit traversal of the primary rays:
+//                   warp-packet traversal (shared stack + votes, the Guenther et al. scheme the
+//                   reference uses on GPUs, intersect.cl:353-575) or per-ray traversal
+//   k_shade         shadePrimaryRayMisses / shadeIndirectRayMisses + shadeHits
+//                   (pt_integrator.cl:17-275) with STABLE compaction of the occlusion and
+//                   indirect rays: warp ballot + popc prefix, block prefix in shared memory and a
+//                   single-pass decoupled look-back across blocks (ticket ordered), so ray order
+//                   == parent ray order, which is what makes bounce >= 1 reproducible
+//   k_occlusion     rayIntersectionTest + accumulateEmissiveSamples (intersect.cl:26-180,
+//                   pt_integrator.cl:278-296)
+//   k_query         rayIntersectionQuery (intersect.cl:184-347) for the indirect rays
+//   k_clear / k_merge / k_tonemap   accumulator.cl:5-19, hdr.cl:5-28
+//
+// The traversal kernels are persistent: the grid is a fixed multiple of the SM count and every
+// warp pulls 32-ray work units from a global queue head (atomicAdd) until the queue, whose length
+// lives in device memory, is empty -- no host round trip between stages (the reference does a
+// clFinish after every launch and two blocking counter writes per bounce).
+#pragma once
+#include "pc_device.cuh"
+
+namespace pc {
+
+constexpr int MAX_BOUNCES = 32;
+constexpr int TRAV_BLOCK = 128;   // 4 warps
+constexpr int SHADE_BLOCK = 256;  // 8 warps
+
+enum StatIdx {
+    ST_QUERY_RAYS = 0, ST_OCCLUSION_RAYS, ST_NODES, ST_TRIS, ST_INSTANCES, ST_SHADED, ST_OCC_EMITTED,
+    ST_IND_EMITTED, ST_UNOCCLUDED, ST_MISSED, ST_COUNT = 16
+};
+
+// Device control block.  [persist] survives a whole pc_trace call, [sample] is zeroed by
+// k_begin_sample.
+struct TraceCtl {
+    int numRays[3];            // [persist] the reference's three ray counters (buffers.go:69)
+    uint32_t nextSample;       // [persist]
+    uint32_t curSample;        // [persist] index of the sample being traced
+    uint32_t pad0[3];
+    unsigned long long stats[ST_COUNT];  // [persist]
+    uint32_t queueHead[2 * MAX_BOUNCES + 2];  // [sample] work-queue heads, one per traversal launch
+    uint32_t ticket[MAX_BOUNCES];             // [sample] block tickets of the shade launches
+};
+
+struct Ray { float4 origin, dir; };                     // types.cl:4-10
+struct PathRec { float4 throughput; uint4 meta; };      // types.cl:12-25 (meta = pixelIndex, flags, -, -)
+struct HitRec { float4 wuvt; uint4 meta; };             // types.cl:69-83 (meta = meshInstance, triIndex, -, -)
+
+struct FrameBufs {
+    Ray *rays[3];
+    PathRec *paths;
+    uint32_t *hitFlags;
+    HitRec *hits;
+    float4 *emissiveSamples;
+    float4 *traceAcc;
+};
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ void warp_add_stat(TraceCtl *ctl, int idx, uint32_t v) {
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if (lane_id() == 0 && v) atomicAdd(&ctl->stats[idx], (unsigned long long)v);
+}
+
+// Pull the next 32-item unit from a queue head; returns the unit's first item index.
+__device__ __forceinline__ uint32_t next_unit(uint32_t *head) {
+    uint32_t u = 0;
+    if (lane_id() == 0) u = atomicAdd(head, 32u);
+    return __shfl_sync(0xFFFFFFFFu, u, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (i == 0) {
+        ctl->curSample = ctl->nextSample;
+        ctl->nextSample = ctl->nextSample + 1;
+    }
+    if (i < 2 * MAX_BOUNCES + 2) ctl->queueHead[i] = 0;
+    if (i < MAX_BOUNCES) ctl->ticket[i] = 0;
+    for (size_t k = i; k < statusWords; k += stride) status[k] = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-packet closest-hit traversal: one node sequence per warp, stack of (reference, lane mask)
+// in shared memory, votes by ballot, front-to-back order by majority.  A lane only works on nodes
+// its own slab test accepted (the mask), so per lane the visited set -- and therefore the hit --
+// is the one the per-ray traversal finds.
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ int traverse_packet(const DScene &sc, uint2 *stack, bool valid, float3 o0, float3 d0,
+                                               float tmaxRay, Hit &best, TravStats &st) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lbit = 1u << lane_id();
+    int sp = 0;
+    float3 o = o0, d = d0;
+    float3 invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    uint32_t curInst = 0, curRank = 0;
+    best.wuvt = make_float4(0.0f, 0.0f, 0.0f, tmaxRay);
+    best.inst = 0; best.tri = 0; best.rank = 0;
+    uint32_t cur = sc.rootRef;
+    unsigned curMask = __ballot_sync(FULL, valid);
+    if (curMask == 0) return 0;
+    for (;;) {
+        const bool mine = (curMask & lbit) != 0;
+        if (!(cur & REF_LEAF)) {
+            const float4 *np = sc.node64 + 4 * (size_t)cur;
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2), q3 = __ldg(np + 3);
+            float tl = FLT_MAX, tr = FLT_MAX;
+            if (mine) {
+                if (COUNT) st.nodes++;
+                tl = slabEntry(xyz(q0), xyz(q1), o, invDir, tmaxRay);
+                tr = slabEntry(xyz(q2), xyz(q3), o, invDir, tmaxRay);
+                float lim = best.wuvt.w * PC_CULL_SLACK;
+                if (tl > lim) tl = FLT_MAX;
+                if (tr > lim) tr = FLT_MAX;
+            }
+            bool wl = tl < FLT_MAX, wr = tr < FLT_MAX;
+            unsigned bl = __ballot_sync(FULL, wl), br = __ballot_sync(FULL, wr);
+            uint32_t lref = f2u(q0.w), rref = f2u(q1.w);
+            if (bl && br) {
+                unsigned prefL = __ballot_sync(FULL, wl && (!wr || tl <= tr));
+                unsigned prefR = __ballot_sync(FULL, wr && (!wl || tr < tl));
+                bool leftFirst = __popc(prefL) >= __popc(prefR);
+                if (lane_id() == 0) stack[sp] = leftFirst ? make_uint2(rref, br) : make_uint2(lref, bl);
+                sp++;
+                cur = leftFirst ? lref : rref;
+                curMask = leftFirst ? bl : br;
+                continue;
+            }
+            if (bl | br) {
+                cur = bl ? lref : rref;
+                curMask = bl ? bl : br;
+                continue;
+            }
+        } else if (cur == REF_POP_INSTANCE) {
+            o = o0; d = d0;
+            invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        } else if (cur & REF_TOP) {
+            curInst = cur & 0x3FFFFFFFu;
+            if (COUNT && mine) st.instances++;
+            const float4 *ip = sc.inst80 + 5 * (size_t)curInst;
+            float4 hdr = __ldg(ip);
+            curRank = f2u(hdr.z);
+            if (!(f2u(hdr.y) & INST_FLAG_IDENTITY)) {
+                float4 m0 = __ldg(ip + 1), m1 = __ldg(ip + 2), m2 = __ldg(ip + 3), m3 = __ldg(ip + 4);
+                o = mul4x1(o, m0, m1, m2, m3);
+                d = mul3x1(d, m0, m1, m2);
+                invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+                if (lane_id() == 0) stack[sp] = make_uint2(REF_POP_INSTANCE, FULL);
+                sp++;
+            }
+            cur = f2u(hdr.x);
+            continue;
+        } else {
+            uint32_t tri = cur & 0x3FFFFFFFu;
+            const float4 *tp = sc.tri48 + 3 * (size_t)tri;
+            float4 a = __ldg(tp);
+            uint32_t count = f2u(a.w);
+            for (;;) {
+                float4 b = __ldg(tp + 1), c = __ldg(tp + 2);
+                if (mine) {
+                    if (COUNT) st.tris++;
+                    float u, v, t;
+                    if (triTest(xyz(a), xyz(b), xyz(c), o, d, u, v, t) && t > PC_EPS) {
+                        float bt = best.wuvt.w;
+                        bool closer = t < bt;
+                        bool tie = (t == bt) && bt < tmaxRay && (curRank < best.rank || (curRank == best.rank && tri < best.tri));
+                        if (closer || tie) {
+                            best.wuvt = make_float4(1.0f - (u + v), u, v, t);
+                            best.tri = tri; best.inst = curInst; best.rank = curRank;
+                        }
+                    }
+                }
+                if (--count == 0) break;
+                tri++;
+                tp += 3;
+                a = __ldg(tp);
+            }
+        }
+        if (sp == 0) break;
+        --sp;
+        __syncwarp();
+        uint2 e = stack[sp];
+        cur = e.x;
+        curMask = e.y;
+        __syncwarp();
+    }
+    return best.wuvt.w < tmaxRay ? 1 : 0;
+}
+
+// MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK) k_primary(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
+                                                       CameraParams cam, uint32_t frameW, uint32_t blockY, uint32_t blockH,
+                                                       uint32_t seedsPerSample, int queueSlot) {
+    __shared__ uint2 s_stack[MODE == 1 ? (TRAV_BLOCK / 32) * PC_STACK_SIZE : 1];
+    const uint32_t n = frameW * blockH;
+    const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->numRays[0] = (int)n;  // camera.cl:24-26
+        atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
+    }
+    const uint32_t tilesX = (frameW + 7) / 8, tilesY = (blockH + 3) / 4;
+    const uint32_t totalItems = MODE == 1 ? tilesX * tilesY * 32u : n;
+    TravStats st{0, 0, 0};
+    uint32_t missed = 0;
+    for (;;) {
+        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+        if (unit >= totalItems) break;
+        uint32_t gx, gy;
+        bool valid;
+        if (MODE == 1) {
+            uint32_t tile = unit / 32u;
+            gx = (tile % tilesX) * 8u + (lane_id() & 7u);
+            gy = (tile / tilesX) * 4u + (lane_id() >> 3);
+            valid = gx < frameW && gy < blockH;
+        } else {
+            uint32_t i = unit + lane_id();
+            valid = i < n;
+            gx = i % frameW;
+            gy = i / frameW;
+        }
+        const uint32_t index = gy * frameW + gx;
+        float3 dir = f3(0.0f, 0.0f, 1.0f);
+        if (valid) {
+            dir = primaryRayDir(cam, gx, gy, blockY, randSeed);
+            fb.rays[0][index].origin = f4(cam.eye, FLT_MAX);  // rayNew (util/ray.cl:13-16)
+            fb.rays[0][index].dir = f4(dir, (float)index);
+            PathRec p;  // pathNew (util/path.cl:13-17)
+            p.throughput = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            p.meta = make_uint4((gy + blockY) * frameW + gx, 0u, 0u, 0u);
+            fb.paths[index] = p;
+        }
+        Hit best;
+        int hit = 0;
+        if (MODE == 1) {
+            hit = traverse_packet<COUNT>(sc, s_stack + (threadIdx.x / 32) * PC_STACK_SIZE, valid, cam.eye, dir, FLT_MAX, best, st);
+        } else if (valid) {
+            hit = MODE == 2 ? traverseReference<false>(sc, cam.eye, dir, FLT_MAX, best)
+                            : traverse<false, COUNT>(sc, cam.eye, dir, FLT_MAX, best, st);
+        }
+        if (valid) {
+            fb.hitFlags[index] = (uint32_t)hit;
+            HitRec h;
+            h.wuvt = best.wuvt;
+            h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
+            fb.hits[index] = h;
+            if (COUNT && !hit) missed++;
+        }
+    }
+    if (COUNT) {
+        warp_add_stat(ctl, ST_NODES, st.nodes);
+        warp_add_stat(ctl, ST_TRIS, st.tris);
+        warp_add_stat(ctl, ST_INSTANCES, st.instances);
+        warp_add_stat(ctl, ST_MISSED, missed);
+    }
+}
+
+// rayIntersectionQuery over rays[a][0 .. numRays[a])
+template <bool REFERENCE, bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK) k_query(DScene sc, const Ray *rays, uint32_t *hitFlags, HitRec *hits,
+                                                     TraceCtl *ctl, int a, int queueSlot) {
+    const uint32_t n = (uint32_t)ctl->numRays[a];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
+    TravStats st{0, 0, 0};
+    uint32_t missed = 0;
+    for (;;) {
+        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+        if (unit >= n) break;
+        uint32_t i = unit + lane_id();
+        if (i < n) {
+            float4 ro = rays[i].origin, rd = rays[i].dir;
+            Hit best;
+            int hit = REFERENCE ? traverseReference<false>(sc, xyz(ro), xyz(rd), ro.w, best)
+                                : traverse<false, COUNT>(sc, xyz(ro), xyz(rd), ro.w, best, st);
+            hitFlags[i] = (uint32_t)hit;
+            HitRec h;
+            h.wuvt = best.wuvt;
+            h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
+            hits[i] = h;
+            if (COUNT && !hit) missed++;
+        }
+    }
+    if (COUNT) {
+        warp_add_stat(ctl, ST_NODES, st.nodes);
+        warp_add_stat(ctl, ST_TRIS, st.tris);
+        warp_add_stat(ctl, ST_INSTANCES, st.instances);
+        warp_add_stat(ctl, ST_MISSED, missed);
+    }
+}
+
+// rayIntersectionTest over rays[2] + accumulateEmissiveSamples for the unoccluded ones.
+// At most one occlusion ray per path and bounce, so the accumulator update needs no atomic
+// (same argument as the reference, pt_integrator.cl:294-295).  hitFlags may be null.
+template <bool REFERENCE, bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
+                                                         const float4 *emissiveSamples, float4 *acc, uint32_t *hitFlags,
+                                                         TraceCtl *ctl, int queueSlot) {
+    const uint32_t n = (uint32_t)ctl->numRays[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)n);
+    TravStats st{0, 0, 0};
+    uint32_t unocc = 0;
+    for (;;) {
+        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+        if (unit >= n) break;
+        uint32_t i = unit + lane_id();
+        if (i < n) {
+            float4 ro = rays[i].origin, rd = rays[i].dir;
+            Hit best;
+            int hit = REFERENCE ? traverseReference<true>(sc, xyz(ro), xyz(rd), ro.w, best)
+                                : traverse<true, COUNT>(sc, xyz(ro), xyz(rd), ro.w, best, st);
+            if (hitFlags) hitFlags[i] = (uint32_t)hit;
+            if (!hit && acc) {
+                uint32_t pathIndex = (uint32_t)rd.w;  // rayGetPathIndex (util/ray.cl:26-28)
+                uint32_t pixel = paths[pathIndex].meta.x;
+                float4 s = emissiveSamples[i];
+                float4 c = acc[pixel];
+                c.x += s.x; c.y += s.y; c.z += s.z;
+                acc[pixel] = c;
+                if (COUNT) unocc++;
+            }
+        }
+    }
+    if (COUNT) {
+        warp_add_stat(ctl, ST_NODES, st.nodes);
+        warp_add_stat(ctl, ST_TRIS, st.tris);
+        warp_add_stat(ctl, ST_INSTANCES, st.instances);
+        warp_add_stat(ctl, ST_UNOCCLUDED, unocc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoupled look-back over the shade blocks' (occlusion, indirect) totals.
+// status word: [63:62] 0 empty / 1 aggregate / 2 inclusive prefix, [61:31] occlusion, [30:0] indirect
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, uint32_t occ, uint32_t ind) {
+    return (flag << 62) | ((unsigned long long)occ << 31) | (unsigned long long)ind;
+}
+__device__ __forceinline__ void lookback(volatile unsigned long long *status, uint32_t ticket, uint32_t occTot,
+                                         uint32_t indTot, uint32_t &occBase, uint32_t &indBase) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = lane_id();
+    if (ticket == 0) {
+        if (lane == 0) status[0] = pack_status(2ull, occTot, indTot);
+        occBase = 0; indBase = 0;
+        return;
+    }
+    if (lane == 0) status[ticket] = pack_status(1ull, occTot, indTot);
+    uint32_t accO = 0, accI = 0;
+    int base = (int)ticket - 1;
+    for (;;) {
+        int idx = base - (int)lane;
+        unsigned long long v = pack_status(2ull, 0u, 0u);  // before block 0: an inclusive prefix of zero
+        if (idx >= 0) {
+            do { v = status[idx]; } while ((v >> 62) == 0ull);
+        }
+        unsigned incMask = __ballot_sync(FULL, (v >> 62) == 2ull);
+        int firstInc = incMask ? (__ffs((int)incMask) - 1) : 32;
+        uint32_t o = 0, i = 0;
+        if ((int)lane <= firstInc) {
+            o = (uint32_t)((v >> 31) & 0x7FFFFFFFull);
+            i = (uint32_t)(v & 0x7FFFFFFFull);
+        }
+        accO += __reduce_add_sync(FULL, o);
+        accI += __reduce_add_sync(FULL, i);
+        if (incMask) break;
+        base -= 32;
+    }
+    occBase = accO; indBase = accI;
+    if (lane == 0) status[ticket] = pack_status(2ull, accO + occTot, accI + indTot);
+}
+
+// shadePrimaryRayMisses / shadeIndirectRayMisses / shadeHits for rays[a][0 .. numRays[a]).
+template <bool COUNT>
+__global__ void __launch_bounds__(SHADE_BLOCK) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
+                                                      unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
+                                                      uint32_t minBouncesForRR, int a, int fixQ4) {
+    __shared__ uint32_t s_occ[SHADE_BLOCK / 32], s_ind[SHADE_BLOCK / 32];
+    __shared__ uint32_t s_ticket, s_occBase, s_indBase;
+    const uint32_t n = (uint32_t)ctl->numRays[a];
+    const uint32_t nBlocks = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // resources.go:230-238: both counters reset
+        ctl->numRays[2] = 0;
+        ctl->numRays[1 - a] = 0;
+    }
+    if (blockIdx.x >= nBlocks) return;
+    // tickets are handed out in scheduling order, so every predecessor of a block is already
+    // resident (or done) when the block looks back: no deadlock under partial residency
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&ctl->ticket[bounce], 1u);
+    __syncthreads();
+    const uint32_t ticket = s_ticket;
+    const uint32_t i = ticket * SHADE_BLOCK + threadIdx.x;
+    const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample + 1 + bounce];
+
+    ShadeOut so;
+    so.wantOcc = false; so.wantInd = false;
+    float pathIndexF = 0.0f;
+    uint32_t shaded = 0;
+    if (i < n) {
+        const float4 rd = fb.rays[a][i].dir;
+        pathIndexF = rd.w;
+        const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
+        if (!fb.hitFlags[i]) {
+            if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
+                float3 kd = shadeMiss(sc, xyz(rd));
+                PathRec p = fb.paths[pathIndex];
+                float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
+                float4 c = fb.traceAcc[p.meta.x];
+                c.x += add.x; c.y += add.y; c.z += add.z;
+                fb.traceAcc[p.meta.x] = c;
+            }
+        } else {
+            shaded = 1;
+            const HitRec h = fb.hits[i];
+            const PathRec p = fb.paths[pathIndex];
+            shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, h.wuvt, h.meta.y, i, bounce, minBouncesForRR, randSeed, so);
+            if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
+            if (so.accum) {
+                const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
+                float4 c = fb.traceAcc[dst];
+                c.x += so.accumAdd.x; c.y += so.accumAdd.y; c.z += so.accumAdd.z;
+                fb.traceAcc[dst] = c;
+            }
+            if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
+        }
+    }
+    // ---- stable compaction (replaces the local/global atomics of pt_integrator.cl:162,176,188-197)
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    const unsigned occMask = __ballot_sync(FULL, so.wantOcc), indMask = __ballot_sync(FULL, so.wantInd);
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint32_t occOff = __popc(occMask & ltMask), indOff = __popc(indMask & ltMask);
+    if (lane == 0) {
+        s_occ[warp] = __popc(occMask);
+        s_ind[warp] = __popc(indMask);
+    }
+    __syncthreads();
+    uint32_t occTot = 0, indTot = 0;
+#pragma unroll
+    for (unsigned w = 0; w < SHADE_BLOCK / 32; w++) {
+        uint32_t oc = s_occ[w], ic = s_ind[w];
+        if (w < warp) { occOff += oc; indOff += ic; }
+        occTot += oc; indTot += ic;
+    }
+    if (warp == 0) {
+        uint32_t ob, ib;
+        lookback(status, ticket, occTot, indTot, ob, ib);
+        if (lane == 0) {
+            s_occBase = ob; s_indBase = ib;
+            if (ticket == nBlocks - 1) {  // last block publishes the queue lengths
+                ctl->numRays[2] = (int)(ob + occTot);
+                ctl->numRays[1 - a] = (int)(ib + indTot);
+                if (COUNT) {
+                    atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(ob + occTot));
+                    atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(ib + indTot));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (so.wantOcc) {  // pt_integrator.cl:200-204
+        const uint32_t k = s_occBase + occOff;
+        fb.emissiveSamples[k] = f4(so.occSample, 0.0f);
+        fb.rays[2][k].origin = f4(so.occOrigin, so.occMaxDist);
+        fb.rays[2][k].dir = f4(so.occDir, pathIndexF);
+    }
+    if (so.wantInd) {  // :207-210
+        const uint32_t k = s_indBase + indOff;
+        fb.rays[1 - a][k].origin = f4(so.indOrigin, FLT_MAX);
+        fb.rays[1 - a][k].dir = f4(so.indDir, pathIndexF);
+    }
+    if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulator.cl:5-19, hdr.cl:5-28
+// ------------------------------------------------------------------------------------------------
+__global__ void k_clear(float4 *acc, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// dst[dstOff + g] += src[srcOff + g]; src may be a peer GPU's memory (loads cross NVLink)
+__global__ void k_merge(float4 *__restrict__ dst, const float4 *__restrict__ src, size_t dstOff, size_t srcOff, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        float4 s = src[srcOff + g];
+        float4 d = dst[dstOff + g];
+        d.x += s.x; d.y += s.y; d.z += s.z;
+        dst[dstOff + g] = d;
+    }
+}
+__global__ void k_tonemap(const float4 *acc, uchar4 *fb, size_t n, float sampleWeight, float exposure) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        fb[i] = tonemapReinhard(acc[i], sampleWeight, exposure);
+}
+
+// ------------------------------------------------------------------------------------------------
+// test hooks
+// ------------------------------------------------------------------------------------------------
+struct BxdfIn { float n[3]; uint32_t matNode; float in[3], p0; float out[3], p1; float rnd[2], uv[2]; };
+struct BxdfOut { float sample[3], samplePdf; float dir[3], pdf; float eval[3], p; };
+__global__ void k_debug_bxdf(DScene sc, const BxdfIn *in, BxdfOut *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Surface s;
+    s.point = f3s(0.0f);
+    s.normal = f3(in[i].n[0], in[i].n[1], in[i].n[2]);
+    s.uv = make_float2(in[i].uv[0], in[i].uv[1]);
+    s.matNodeIndex = in[i].matNode;
+    MatNode m = loadMatNode(sc, in[i].matNode);
+    float3 inDir = f3(in[i].in[0], in[i].in[1], in[i].in[2]), outDir = f3(in[i].out[0], in[i].out[1], in[i].out[2]);
+    float3 dir = f3s(0.0f);
+    float pdf = 1.0f;
+    float3 smp = bxdfGetSample(s, m, sc, make_float2(in[i].rnd[0], in[i].rnd[1]), inDir, dir, pdf);
+    float p = bxdfGetPdf(s, m, sc, inDir, outDir);
+    float3 ev = bxdfEval(s, m, sc, inDir, outDir);
+    BxdfOut o = {{smp.x, smp.y, smp.z}, pdf, {dir.x, dir.y, dir.z}, p, {ev.x, ev.y, ev.z}, 0.0f};
+    out[i] = o;
+}
+__global__ void k_debug_rng(uint2 *states, uint32_t n, uint32_t draws, float2 *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint2 s = states[i];
+    for (uint32_t d = 0; d < draws; d++) out[(size_t)i * draws + d] = randomGetSample2f(s);
+    states[i] = s;
+}
+// primary-style packet traversal over an arbitrary ray list (32 consecutive rays per packet)
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK) k_debug_packet(DScene sc, const Ray *rays, uint32_t *hitFlags, HitRec *hits,
+                                                            TraceCtl *ctl, uint32_t n, int queueSlot) {
+    __shared__ uint2 s_stack[(TRAV_BLOCK / 32) * PC_STACK_SIZE];
+    TravStats st{0, 0, 0};
+    for (;;) {
+        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+        if (unit >= n) break;
+        uint32_t i = unit + lane_id();
+        bool valid = i < n;
+        float4 ro = make_float4(0.f, 0.f, 0.f, 0.f), rd = make_float4(0.f, 0.f, 1.f, 0.f);
+        if (valid) { ro = rays[i].origin; rd = rays[i].dir; }
+        Hit best;
+        int hit = traverse_packet<COUNT>(sc, s_stack + (threadIdx.x / 32) * PC_STACK_SIZE, valid, xyz(ro), xyz(rd), ro.w, best, st);
+        if (valid) {
+            hitFlags[i] = (uint32_t)hit;
+            HitRec h;
+            h.wuvt = best.wuvt;
+            h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
+            hits[i] = h;
+        }
+    }
+    if (COUNT) {
+        warp_add_stat(ctl, ST_NODES, st.nodes);
+        warp_add_stat(ctl, ST_TRIS, st.tris);
+        warp_add_stat(ctl, ST_INSTANCES, st.instances);
+    }
+}
+
+}  // namespace pc

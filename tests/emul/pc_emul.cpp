@@ -1,0 +1,270 @@
+// pc_emul.cpp -- TEST-ONLY host build of the CUDA tracer's per-ray device functions.
+//
+// polaris_b200/csrc/pc_device.cuh is written host+device portable.  This harness compiles it
+// with g++ and drives it with plain loops so the CPU-only test tier can compare the CUDA
+// side's traversal (derived node64/tri48 layout, near-first order, culling, tie-break) and
+// shading code with the oracle without a GPU.  With the same libm on both sides the results
+// are expected to be bit-identical.  It is not a fallback: nothing in polaris_b200/ loads it.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/polaris_cuda.h"
+#include "../../polaris_b200/csrc/pc_device.cuh"
+#include "../../polaris_b200/csrc/pc_layout.hpp"
+
+using namespace pc;
+
+namespace {
+struct Ray { float4 origin, dir; };
+struct PathRec { float4 throughput; uint32_t pixelIndex, flags, r1, r2; };
+struct HitRec { float4 wuvt; uint32_t inst, tri, r1, r2; };
+
+struct Emul {
+    pc_layout::Layout layout;
+    DScene sc{};
+    uint32_t W = 0, H = 0;
+    CameraParams cam{};
+    std::vector<Ray> rays[3];
+    std::vector<PathRec> paths;
+    std::vector<uint32_t> flags;
+    std::vector<HitRec> hits;
+    std::vector<float4> emissiveSamples, traceAcc;
+    int numRays[3] = {0, 0, 0};
+    std::string error;
+};
+}  // namespace
+
+extern "C" {
+
+void *pe_create(const pc_scene_view *v) {
+    auto *e = new Emul();
+    pc_layout::Builder b((const pc_layout::RefNode *)v->bvh_nodes, v->bvh_nodes_bytes / 32,
+                         (const pc_layout::RefInstance *)v->mesh_instances, v->mesh_instances_bytes / 80,
+                         (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16);
+    e->layout = b.build();
+    e->error = e->layout.error;
+    DScene &s = e->sc;
+    s.node64 = (const float4 *)e->layout.node64.data();
+    s.tri48 = (const float4 *)e->layout.tri48.data();
+    s.inst80 = (const float4 *)e->layout.inst80.data();
+    s.rootRef = e->layout.root_ref;
+    s.bvhNodes = (const float4 *)v->bvh_nodes;
+    s.meshInstances = (const float4 *)v->mesh_instances;
+    s.vertices = (const float4 *)v->vertices;
+    s.normals = (const float4 *)v->normals;
+    s.uvs = (const float2 *)v->uvs;
+    s.matIndex = (const uint32_t *)v->material_indices;
+    s.matNodes = (const float4 *)v->material_nodes;
+    s.emissives = (const float4 *)v->emissives;
+    s.texMeta = (const uint4 *)v->texture_metadata;
+    s.texData = (const uint8_t *)v->texture_data;
+    s.numEmissives = (uint32_t)(v->emissives_bytes / 80);
+    s.sceneDiffuseMat = v->scene_diffuse_mat_index;
+    return e;
+}
+void pe_destroy(void *h) { delete (Emul *)h; }
+const char *pe_error(void *h) { return ((Emul *)h)->error.empty() ? nullptr : ((Emul *)h)->error.c_str(); }
+void pe_layout_info(void *h, int *top_depth, int *mesh_depth, int *stack_need, uint32_t *inner_nodes) {
+    Emul &e = *(Emul *)h;
+    *top_depth = e.layout.top_depth; *mesh_depth = e.layout.mesh_depth; *stack_need = e.layout.stack_need;
+    *inner_nodes = (uint32_t)(e.layout.node64.size() / 4);
+}
+
+// mode 0: closest hit (derived layout), 1: any hit, 2: closest hit reference order, 3: any hit reference order
+int pe_intersect(void *h, const void *rays_in, uint32_t n, int mode, uint32_t *out_flags, void *out_hits, uint64_t *counters) {
+    Emul &e = *(Emul *)h;
+    if (e.layout.stack_need > PC_STACK_SIZE) return PC_ERR_STACK_DEPTH;
+    const Ray *rays = (const Ray *)rays_in;
+    HitRec *hits = (HitRec *)out_hits;
+    uint64_t nodes = 0, tris = 0, inst = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nodes, tris, inst)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        Hit best;
+        TravStats st{0, 0, 0};
+        float3 o = xyz(rays[i].origin), d = xyz(rays[i].dir);
+        float tmax = rays[i].origin.w;
+        int f;
+        switch (mode) {
+            case 0: f = traverse<false, true>(e.sc, o, d, tmax, best, st); break;
+            case 1: f = traverse<true, true>(e.sc, o, d, tmax, best, st); break;
+            case 2: f = traverseReference<false>(e.sc, o, d, tmax, best); break;
+            default: f = traverseReference<true>(e.sc, o, d, tmax, best); break;
+        }
+        out_flags[i] = (uint32_t)f;
+        if (hits && (mode == 0 || mode == 2)) hits[i] = HitRec{best.wuvt, best.inst, best.tri, 0, 0};
+        nodes += st.nodes; tris += st.tris; inst += st.instances;
+    }
+    if (counters) { counters[0] = nodes; counters[1] = tris; counters[2] = inst; }
+    return 0;
+}
+
+int pe_resize(void *h, uint32_t w, uint32_t hh) {
+    Emul &e = *(Emul *)h;
+    e.W = w; e.H = hh;
+    size_t px = (size_t)w * hh;
+    for (auto &r : e.rays) r.assign(px, Ray{});
+    e.paths.assign(px, PathRec{});
+    e.flags.assign(px, 0);
+    e.hits.assign(px, HitRec{});
+    e.emissiveSamples.assign(px, make_float4(0, 0, 0, 0));
+    e.traceAcc.assign(px, make_float4(0, 0, 0, 0));
+    return 0;
+}
+int pe_set_camera(void *h, const float eye[3], const float fr[16]) {
+    Emul &e = *(Emul *)h;
+    e.cam.eye = f3(eye[0], eye[1], eye[2]);
+    memcpy(&e.cam.frustrumTL, fr, 64);
+    return 0;
+}
+
+// The sample / bounce loops of tracer.go:194-247 + pipeline.go:94-213 over the device functions,
+// in the fused stage order the CUDA kernels use (miss+hit shading, occlusion+accumulate).
+int pe_trace(void *h, pc_block_request *req, const uint32_t *seeds, size_t n_seeds) {
+    Emul &e = *(Emul *)h;
+    const DScene &sc = e.sc;
+    const size_t per = 1 + (size_t)req->num_bounces;
+    if (n_seeds < per * req->samples_per_pixel) return PC_ERR_INVALID_ARGUMENT;
+    std::fill(e.traceAcc.begin(), e.traceAcc.end(), make_float4(0, 0, 0, 0));
+    e.cam.texelDims = make_float2(1.0f / (float)req->frame_w, 1.0f / (float)req->frame_h);
+    const uint32_t W = req->frame_w, BH = req->block_h, BY = req->block_y;
+    std::vector<ShadeOut> so((size_t)W * BH);
+    std::vector<uint8_t> shaded((size_t)W * BH);
+    for (uint32_t s = 0; s < req->samples_per_pixel; s++) {
+        const uint32_t *ss = seeds + per * s;
+        req->seed = ss[0];
+        int n = (int)(W * BH);
+        e.numRays[0] = n;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int i = 0; i < n; i++) {
+            uint32_t gx = (uint32_t)i % W, gy = (uint32_t)i / W;
+            float3 d = primaryRayDir(e.cam, gx, gy, BY, ss[0]);
+            e.rays[0][i].origin = f4(e.cam.eye, FLT_MAX);
+            e.rays[0][i].dir = f4(d, (float)i);
+            e.paths[i] = PathRec{make_float4(1.0f, 1.0f, 1.0f, 0.0f), (gy + BY) * W + gx, 0, 0, 0};
+            Hit best; TravStats st{0, 0, 0};
+            e.flags[i] = (uint32_t)traverse<false, false>(sc, e.cam.eye, d, FLT_MAX, best, st);
+            e.hits[i] = HitRec{best.wuvt, best.inst, best.tri, 0, 0};
+        }
+        int a = 0;
+        for (uint32_t bounce = 0; bounce < req->num_bounces; bounce++) {
+            n = e.numRays[a];
+#pragma omp parallel for schedule(dynamic, 256)
+            for (int i = 0; i < n; i++) {
+                shaded[i] = 0;
+                const Ray &r = e.rays[a][i];
+                uint32_t pathIdx = (uint32_t)r.dir.w;
+                PathRec &p = e.paths[pathIdx];
+                if (!e.flags[i]) {
+                    if (sc.sceneDiffuseMat != -1) {
+                        float3 kd = shadeMiss(sc, xyz(r.dir));
+                        float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
+                        float4 &acc = e.traceAcc[p.pixelIndex];
+                        acc.x += add.x; acc.y += add.y; acc.z += add.z;
+                    }
+                    continue;
+                }
+                shaded[i] = 1;
+                shadeHit(sc, xyz(r.dir), xyz(p.throughput), p.flags, e.hits[i].wuvt, e.hits[i].tri, (uint32_t)i, bounce,
+                         req->min_bounces_for_rr, ss[1 + bounce], so[i]);
+                if (so[i].flagsChanged) p.flags = so[i].pathFlags;
+                if (so[i].accum) {
+                    float4 &acc = e.traceAcc[p.pixelIndex];
+                    acc.x += so[i].accumAdd.x; acc.y += so[i].accumAdd.y; acc.z += so[i].accumAdd.z;
+                }
+                if (so[i].wantInd) p.throughput = f4(so[i].newThroughput, p.throughput.w);
+            }
+            int nOcc = 0, nInd = 0;
+            for (int i = 0; i < n; i++) {
+                if (!shaded[i]) continue;
+                float pathIdx = e.rays[a][i].dir.w;
+                if (so[i].wantOcc) {
+                    e.emissiveSamples[nOcc] = f4(so[i].occSample, 0.0f);
+                    e.rays[2][nOcc] = Ray{f4(so[i].occOrigin, so[i].occMaxDist), f4(so[i].occDir, pathIdx)};
+                    nOcc++;
+                }
+                if (so[i].wantInd) e.rays[1 - a][nInd++] = Ray{f4(so[i].indOrigin, FLT_MAX), f4(so[i].indDir, pathIdx)};
+            }
+            e.numRays[2] = nOcc;
+            e.numRays[1 - a] = nInd;
+            std::vector<uint8_t> occl(nOcc);
+#pragma omp parallel for schedule(dynamic, 256)
+            for (int i = 0; i < nOcc; i++) {
+                Hit best; TravStats st{0, 0, 0};
+                const Ray &r = e.rays[2][i];
+                occl[i] = (uint8_t)traverse<true, false>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+            }
+            for (int i = 0; i < nOcc; i++) {
+                if (occl[i]) continue;
+                uint32_t pathIdx = (uint32_t)e.rays[2][i].dir.w;
+                float4 &acc = e.traceAcc[e.paths[pathIdx].pixelIndex];
+                acc.x += e.emissiveSamples[i].x; acc.y += e.emissiveSamples[i].y; acc.z += e.emissiveSamples[i].z;
+            }
+            if (bounce + 1 < req->num_bounces) {
+                a = 1 - a;
+                n = e.numRays[a];
+#pragma omp parallel for schedule(dynamic, 256)
+                for (int i = 0; i < n; i++) {
+                    Hit best; TravStats st{0, 0, 0};
+                    const Ray &r = e.rays[a][i];
+                    e.flags[i] = (uint32_t)traverse<false, false>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+                    e.hits[i] = HitRec{best.wuvt, best.inst, best.tri, 0, 0};
+                }
+            }
+        }
+        req->accumulated_samples++;
+    }
+    return 0;
+}
+
+int pe_read_buffer(void *h, int which, void *dst, uint64_t bytes) {
+    Emul &e = *(Emul *)h;
+    const void *src = nullptr;
+    switch (which) {
+        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: src = e.rays[which].data(); break;
+        case PC_BUF_PATHS: src = e.paths.data(); break;
+        case PC_BUF_HIT_FLAGS: src = e.flags.data(); break;
+        case PC_BUF_INTERSECTIONS: src = e.hits.data(); break;
+        case PC_BUF_EMISSIVE_SAMPLES: src = e.emissiveSamples.data(); break;
+        case PC_BUF_TRACE_ACCUMULATOR: src = e.traceAcc.data(); break;
+        case PC_BUF_RAY_COUNTERS: src = e.numRays; break;
+        default: return PC_ERR_INVALID_ARGUMENT;
+    }
+    memcpy(dst, src, bytes);
+    return 0;
+}
+
+struct BxdfIn { float n[3]; uint32_t matNode; float in[3], p0; float out[3], p1; float rnd[2], uv[2]; };
+struct BxdfOut { float sample[3], samplePdf; float dir[3], pdf; float eval[3], p; };
+int pe_bxdf(void *h, const void *in_records, uint32_t n, void *out_records) {
+    Emul &e = *(Emul *)h;
+    const BxdfIn *in = (const BxdfIn *)in_records;
+    BxdfOut *out = (BxdfOut *)out_records;
+    for (uint32_t i = 0; i < n; i++) {
+        Surface s;
+        s.point = f3s(0.0f);
+        s.normal = f3(in[i].n[0], in[i].n[1], in[i].n[2]);
+        s.uv = make_float2(in[i].uv[0], in[i].uv[1]);
+        s.matNodeIndex = in[i].matNode;
+        MatNode m = loadMatNode(e.sc, in[i].matNode);
+        float3 inDir = f3(in[i].in[0], in[i].in[1], in[i].in[2]), outDir = f3(in[i].out[0], in[i].out[1], in[i].out[2]);
+        float3 dir = f3s(0.0f);
+        float pdf = 1.0f;
+        float3 smp = bxdfGetSample(s, m, e.sc, make_float2(in[i].rnd[0], in[i].rnd[1]), inDir, dir, pdf);
+        float p = bxdfGetPdf(s, m, e.sc, inDir, outDir);
+        float3 ev = bxdfEval(s, m, e.sc, inDir, outDir);
+        out[i] = BxdfOut{{smp.x, smp.y, smp.z}, pdf, {dir.x, dir.y, dir.z}, p, {ev.x, ev.y, ev.z}, 0.0f};
+    }
+    return 0;
+}
+
+int pe_tonemap(const float *acc, uint32_t n, float w, float exposure, uint8_t *rgba) {
+    for (uint32_t i = 0; i < n; i++) {
+        uchar4 c = tonemapReinhard(make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], 0.0f), w, exposure);
+        rgba[4 * i] = c.x; rgba[4 * i + 1] = c.y; rgba[4 * i + 2] = c.z; rgba[4 * i + 3] = c.w;
+    }
+    return 0;
+}
+
+}  // extern "C"
