@@ -507,6 +507,7 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
         for (auto &x : own) x = next_seed(tr->seedState);
         seeds = own.data();
     }
+    tr->cam.texelDims = make_float2(1.0f / (float)req->frame_w, 1.0f / (float)req->frame_h);  // resources.go:130-133
     cudaStream_t s = tr->stream;
     // pipeline.Reset -> ClearFrameAccumulator when the sample counter was reset (tracer.go:208-213)
     if (req->accumulated_samples == 0 && !tr->frameOpenByMerge) {

@@ -90,7 +90,8 @@ def test_hit_records_bit_exact(key, w, h):
     # occlusion: rays with a finite max distance
     occ = rays.copy()
     t = oh["wuvt"][:, 3]
-    occ["origin"][:, 3] = np.where(of == 1, t * np.float32(0.5) + np.float32(0.5) * t * (np.arange(len(t)) % 3 == 0), np.float32(3.0))
+    # max distance before the first hit for a third of the rays (unoccluded), beyond it for the rest
+    occ["origin"][:, 3] = np.where(of == 1, t * np.where(np.arange(len(t)) % 3 == 0, np.float32(0.5), np.float32(1.5)), np.float32(3.0))
     of1, _ = orc.debug_intersect(occ, 1)
     gf1, _ = cu.debug_intersect(occ, 1)
     assert (gf1 == of1).all()
@@ -204,9 +205,11 @@ def test_merge_blocks_two_handles():
     seeds = [T.splitmix_seeds(10 + i, spp * 6) for i in range(2)]
     cus = [C.cuda_for(sc, w, h), C.cuda_for(sc, w, h)]
     orcs = [C.oracle_for(sc, w, h), C.oracle_for(sc, w, h)]
-    for trs in (cus, orcs):
-        # non-primary finishes first: its merge must not be wiped by the primary's own reset
-        for i in (1, 0):
+    for trs, order in ((cus, (1, 0)), (orcs, (0, 1))):
+        # CUDA: the non-primary finishes first and its merge must survive the primary's own first-pass
+        # reset (the reference -- and therefore the oracle -- wipes it: SURVEY Q17, tracer.go:208-213);
+        # the oracle is driven in the race-free order, seeds are per tracer so the frames are equal
+        for i in order:
             by, bh = blocks[i]
             r = T.make_block_request(w, h, block_y=by, block_h=bh, spp=spp)
             trs[i].trace(r, seeds[i])
