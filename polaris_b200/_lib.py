@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolaris_cuda.so")
+LIB_PATH = os.environ.get("POLARIS_CUDA_LIB") or os.path.join(_HERE, "libpolaris_cuda.so")  # env override: A/B builds only
 
 u32, u64, i32, f32 = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int32, ctypes.c_float
 vp = ctypes.c_void_p

@@ -35,7 +35,8 @@ struct DScene {
 
 constexpr uint32_t REF_LEAF = 0x80000000u;
 constexpr uint32_t REF_TOP = 0x40000000u;
-constexpr uint32_t REF_POP_INSTANCE = 0xFFFFFFFFu;
+constexpr uint32_t REF_POP_INSTANCE = 0xFFFFFFFFu;  // stack marker: restore the world-space ray
+constexpr uint32_t REF_DONE = 0xFFFFFFFEu;          // traversal finished (never stored)
 constexpr uint32_t INST_FLAG_IDENTITY = 1u;
 
 // bxdf.cl:10-21, material_sampler.cl:4-9, path.cl:4-6, emissive_sampler.cl:4-5, texture_sampler.cl:4-7
@@ -105,7 +106,7 @@ PC_HD float3 mul3x1(float3 v, float4 m0, float4 m1, float4 m2) {
     o.z = m0.z * v.x + m1.z * v.y + m2.z * v.z;
     return o;
 }
-PC_HD float2 rayToLatLongUV(float3 v) {
+PC_HD_NOINLINE float2 rayToLatLongUV(float3 v) {
     float at2 = atan2f(v.x, v.z);
     float r = length(v);
     return make_float2((at2 >= 0.0f ? at2 : (at2 + PC_TWO_PI)) / PC_TWO_PI, acosf(v.y / r) / PC_PI);
@@ -141,8 +142,8 @@ struct TexTaps {
     float cx, cy;
     const uint8_t *base;
 };
-PC_HD TexTaps texTaps(float2 uv, int texIndex, const DScene &sc) {  // :15-36
-    uint4 m = PC_LDG(sc.texMeta + texIndex);                         // format, width, height, dataOffset
+PC_HD TexTaps texTaps(float2 uv, int texIndex, const uint4 *texMeta, const uint8_t *texData) {  // :15-36
+    uint4 m = PC_LDG(texMeta + texIndex);  // format, width, height, dataOffset
     TexTaps t;
     float sx = uv.x - floorf(uv.x), sy = uv.y - floorf(uv.y);
     sx *= (float)m.y;
@@ -155,7 +156,7 @@ PC_HD TexTaps texTaps(float2 uv, int texIndex, const DScene &sc) {  // :15-36
     t.cy = sy - (float)t.ty;
     t.w = m.y;
     t.format = m.x;
-    t.base = sc.texData + m.w;
+    t.base = texData + m.w;
     return t;
 }
 PC_HD float ldF(const uint8_t *p) { return PC_LDG((const float *)p); }
@@ -170,8 +171,8 @@ PC_HD float4 ldRGBA8(const uint8_t *base, uint32_t i) {
     return make_float4((float)(v & 255u), (float)((v >> 8) & 255u), (float)((v >> 16) & 255u), (float)(v >> 24));
 }
 
-PC_HD float3 texGetSample3f(float2 uv, int texIndex, const DScene &sc) {  // :14-101
-    TexTaps t = texTaps(uv, texIndex, sc);
+PC_HD_NOINLINE float3 texSample3(float2 uv, int texIndex, const uint4 *texMeta, const uint8_t *texData) {  // :14-101
+    TexTaps t = texTaps(uv, texIndex, texMeta, texData);
     uint32_t iTL = t.ty * t.w + t.tx, iTR = t.ty * t.w + t.bx, iBL = t.by * t.w + t.tx, iBR = t.by * t.w + t.bx;
     switch (t.format) {
         case TEX_RGBA8: {
@@ -206,16 +207,16 @@ PC_HD float texRed(const TexTaps &t, uint32_t i) {
     }
     return 0.0f;
 }
-PC_HD float texGetSample1f(float2 uv, int texIndex, const DScene &sc) {  // :105-184
-    TexTaps t = texTaps(uv, texIndex, sc);
+PC_HD_NOINLINE float texSample1(float2 uv, int texIndex, const uint4 *texMeta, const uint8_t *texData) {  // :105-184
+    TexTaps t = texTaps(uv, texIndex, texMeta, texData);
     if (t.format > TEX_RGBA32F) return 0.0f;
     float a = texRed(t, t.ty * t.w + t.tx), b = texRed(t, t.ty * t.w + t.bx);
     float c = texRed(t, t.by * t.w + t.tx), d = texRed(t, t.by * t.w + t.bx);
     float r = mix(mix(a, c, t.cy), mix(b, d, t.cy), t.cx);
     return (t.format == TEX_RGBA8 || t.format == TEX_L8) ? r / 255.0f : r;
 }
-PC_HD float3 texGetBumpSample3f(float2 uv, int texIndex, const DScene &sc) {  // :187-251
-    TexTaps t = texTaps(uv, texIndex, sc);
+PC_HD_NOINLINE float3 texBump3(float2 uv, int texIndex, const uint4 *texMeta, const uint8_t *texData) {  // :187-251
+    TexTaps t = texTaps(uv, texIndex, texMeta, texData);
     if (t.format > TEX_RGBA32F) return f3(0.0f, 0.0f, 0.0f);
     float s0 = texRed(t, t.ty * t.w + t.tx), s1 = texRed(t, t.ty * t.w + t.bx), s2 = texRed(t, t.by * t.w + t.tx);
     if (t.format == TEX_RGBA8 || t.format == TEX_L8) {
@@ -223,6 +224,10 @@ PC_HD float3 texGetBumpSample3f(float2 uv, int texIndex, const DScene &sc) {  //
     }
     return f3(0.5f, 0.5f, 0.5f) + 0.5f * normalize(f3(s1 - s0, s2 - s0, 1.0f));
 }
+
+PC_HD float3 texGetSample3f(float2 uv, int texIndex, const DScene &sc) { return texSample3(uv, texIndex, sc.texMeta, sc.texData); }
+PC_HD float texGetSample1f(float2 uv, int texIndex, const DScene &sc) { return texSample1(uv, texIndex, sc.texMeta, sc.texData); }
+PC_HD float3 texGetBumpSample3f(float2 uv, int texIndex, const DScene &sc) { return texBump3(uv, texIndex, sc.texMeta, sc.texData); }
 
 // ------------------------------------------------------------------------------------------------
 // samplers/material_sampler.cl
@@ -326,7 +331,7 @@ PC_HD float ggxGetD(float roughness, float3 n, float3 m) {  // :38-52
     float denom = PC_PI * nDotMSq * nDotMSq * (aSq + tanSq) * (aSq + tanSq);
     return denom > 0.0f ? (aSq / denom) : 0.0f;
 }
-PC_HD float3 ggxGetSample(float roughness, float3 n, float2 r) {  // :55-74 (sinPhi >= 0: SURVEY Q8)
+PC_HD_NOINLINE float3 ggxGetSample(float roughness, float3 n, float2 r) {  // :55-74 (sinPhi >= 0: SURVEY Q8)
     float3 u, v;
     tangentVectors(n, u, v);
     float theta = atanf(roughness * sqrtf(r.x / (1.0f - r.x)));
@@ -337,20 +342,20 @@ PC_HD float3 ggxGetSample(float roughness, float3 n, float2 r) {  // :55-74 (sin
     float sinPhi = sqrtf(1.0f - cosPhi * cosPhi);
     return normalize(u * sinTheta * cosPhi + v * sinTheta * sinPhi + n * cosTheta);
 }
-PC_HD float ggxGetReflectionPdf(float roughness, float3 o, float3 n, float3 h) {  // :76-85
+PC_HD_NOINLINE float ggxGetReflectionPdf(float roughness, float3 o, float3 n, float3 h) {  // :76-85
     float nDotH = fabsf(dot(n, h));
     float oDotH = fabsf(dot(o, h));
     float denom = 4.0f * oDotH;
     return denom == 0.0f ? 0.0f : ggxGetD(roughness, n, h) * nDotH / denom;
 }
-PC_HD float ggxGetRefractionPdf(float roughness, float etaI, float etaT, float3 i, float3 o, float3 n, float3 h) {  // :87-96
+PC_HD_NOINLINE float ggxGetRefractionPdf(float roughness, float etaI, float etaT, float3 i, float3 o, float3 n, float3 h) {  // :87-96
     float iDotH = fabsf(dot(i, h));
     float oDotH = fabsf(dot(o, h));
     float hDotN = fabsf(dot(h, n));
     float denom = (etaI * iDotH + etaT * oDotH) * (etaI * iDotH + etaT * oDotH);
     return denom > 0.0f ? ggxGetD(roughness, n, h) * hDotN * oDotH * etaT * etaT / denom : 0.0f;
 }
-PC_HD float3 cosWeightedHemisphereGetSample(float3 normal, float2 r) {  // :101-112
+PC_HD_NOINLINE float3 cosWeightedHemisphereGetSample(float3 normal, float2 r) {  // :101-112
     float rd = sqrtf(r.x);
     float phi = PC_TWO_PI * r.y;
     float3 u, v;
@@ -371,7 +376,7 @@ PC_HD float conductorFresnel(const MatNode &m, float iDotN) {
 }
 // GGX reflection lobe shared by roughConductor and the reflected branch of roughDielectric
 // (rough_conductor.cl:36-39,61-77; rough_dielectric.cl:41-55,135-146)
-PC_HD float3 ggxReflectionEval(float roughness, float3 ks, float f, float3 i, float3 o, float3 n) {
+PC_HD_NOINLINE float3 ggxReflectionEval(float roughness, float3 ks, float f, float3 i, float3 o, float3 n) {
     float iDotN = dot(i, n);
     float oDotN = dot(o, n);
     float3 h = normalize(i + o);
@@ -380,19 +385,19 @@ PC_HD float3 ggxReflectionEval(float roughness, float3 ks, float f, float3 i, fl
     float denom = 4.0f * iDotN * oDotN;
     return denom > 0.0f ? ks * f * d * g / denom : f3s(0.0f);
 }
-// equation 21 of Walter et al. as written in rough_dielectric.cl:59-82,148-165
-PC_HD float3 ggxRefractionEval(float roughness, float3 tfDefault, int tfTex, float f, float etaI, float etaT, float3 i,
-                               float3 o, float3 h, const Surface &s, const DScene &sc) {
-    float iDotN = dot(i, s.normal);
-    float oDotN = dot(o, s.normal);
+// equation 21 of Walter et al. as written in rough_dielectric.cl:59-82,148-165 (tf is the
+// transmittance sample; the reference fetches it after the zero-denominator test, it is pure)
+PC_HD_NOINLINE float3 ggxRefractionEval(float roughness, float3 tf, float f, float etaI, float etaT, float3 i, float3 o,
+                                        float3 h, float3 n) {
+    float iDotN = dot(i, n);
+    float oDotN = dot(o, n);
     float iDotH = fabsf(dot(i, h));
     float oDotH = fabsf(dot(o, h));
     float focusTermDenom = iDotN * oDotN * (etaI * iDotH + etaT * oDotH) * (etaI * iDotH + etaT * oDotH);
     if (focusTermDenom == 0.0f) return f3(0.0f, 0.0f, 0.0f);
     float focusTerm = fabsf(etaT * etaT * iDotH * oDotH / focusTermDenom);
-    float d = ggxGetD(roughness, s.normal, h);
-    float g = ggxGetG(roughness, i, o, s.normal, h);
-    float3 tf = matGetSample3f(s.uv, tfDefault, tfTex, sc);
+    float d = ggxGetD(roughness, n, h);
+    float g = ggxGetG(roughness, i, o, n, h);
     return tf * (1.0f - f) * d * g * focusTerm;
 }
 
@@ -459,7 +464,7 @@ PC_HD float3 bxdfGetSample(const Surface &s, const MatNode &m, const DScene &sc,
             out = (eta * iDotN - cl_sign(iDotN) * sqrtf(cosTSq)) * h - eta * in;
             h = normalize(-(etaI * in + etaT * out));
             pdf = ggxGetRefractionPdf(roughness, etaI, etaT, in, out, n, h);
-            return ggxRefractionEval(roughness, m.u3, m.rightOrTransTex, f, etaI, etaT, in, out, h, s, sc);
+            return ggxRefractionEval(roughness, matGetSample3f(s.uv, m.u3, m.rightOrTransTex, sc), f, etaI, etaT, in, out, h, n);
         }
     }
     return f3(0.0f, 0.0f, 0.0f);
@@ -529,7 +534,7 @@ PC_HD float3 bxdfEval(const Surface &s, const MatNode &m, const DScene &sc, floa
                 return ggxReflectionEval(roughness, ks, f, in, out, n);
             }
             float3 h = normalize(-(etaI * in + etaT * out));
-            return ggxRefractionEval(roughness, m.u3, m.rightOrTransTex, f, etaI, etaT, in, out, h, s, sc);
+            return ggxRefractionEval(roughness, matGetSample3f(s.uv, m.u3, m.rightOrTransTex, sc), f, etaI, etaT, in, out, h, n);
         }
     }
     return f3(0.0f, 0.0f, 0.0f);
@@ -712,7 +717,10 @@ PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &b
     best.inst = 0; best.tri = 0; best.rank = 0;
     uint32_t cur = sc.rootRef;
     for (;;) {
-        if (!(cur & REF_LEAF)) {
+        // ---- phase 1: walk inner nodes until the current reference is a leaf-type one.  Keeping
+        // the two phases in separate loops lets a warp reconverge on "all lanes test boxes" /
+        // "all lanes test triangles" instead of interleaving both bodies lane by lane.
+        while (!(cur & REF_LEAF)) {
             if (COUNT) st.nodes++;
             const float4 *np = sc.node64 + 4 * (size_t)cur;
             float4 q0 = PC_LDG(np), q1 = PC_LDG(np + 1), q2 = PC_LDG(np + 2), q3 = PC_LDG(np + 3);
@@ -729,13 +737,15 @@ PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &b
                 bool leftFirst = tl <= tr;
                 stack[sp++] = leftFirst ? rref : lref;
                 cur = leftFirst ? lref : rref;
-                continue;
-            }
-            if (wl || wr) {
+            } else if (wl || wr) {
                 cur = wl ? lref : rref;
-                continue;
+            } else {
+                cur = sp ? stack[--sp] : REF_DONE;
             }
-        } else if (cur == REF_POP_INSTANCE) {  // left the instance (:330-335)
+        }
+        if (cur == REF_DONE) break;
+        // ---- phase 2: leaf-type references
+        if (cur == REF_POP_INSTANCE) {  // left the instance (:330-335)
             o = o0; d = d0;
             invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
         } else if (cur & REF_TOP) {  // top-level leaf: enter the instance (:237-249)

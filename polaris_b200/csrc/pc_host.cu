@@ -91,7 +91,7 @@ struct pc_tracer {
     bool frameOpen = false, frameOpenByMerge = false;
     pc_stats stats{};
     uint64_t seedState = 0x501A2150ull;
-    int persistentGrid = 0;
+    int persistentGrid = 0, shadeGrid = 0;
 };
 
 namespace {
@@ -176,7 +176,8 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
     const uint32_t nb = req.num_bounces, perSample = 1 + nb;
     const uint32_t N = req.frame_w * req.block_h;
     const int pg = tr->persistentGrid;
-    const int shadeGrid = (int)((N + SHADE_BLOCK - 1) / SHADE_BLOCK);
+    const int shadeGrid = tr->shadeGrid;
+    (void)N;
     uint64_t L = 0;
     size_t statusWords = tr->statusStride * nb;
     {
@@ -319,6 +320,10 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     if (perSM < 1) perSM = 1;
     if (perSM > 8) perSM = 8;
     tr->persistentGrid = tr->prop.multiProcessorCount * perSM;
+    int shadePerSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
+    if (shadePerSM < 1) shadePerSM = 1;
+    tr->shadeGrid = tr->prop.multiProcessorCount * shadePerSM;
     tr->sc.sceneDiffuseMat = -1;
     *out = tr;
     return 0;
@@ -394,7 +399,7 @@ int pc_resize(pc_tracer *tr, uint32_t w, uint32_t h) {
     CU(tr, PC_ERR_ALLOC, tr->frameAcc.alloc(px * 16));
     CU(tr, PC_ERR_ALLOC, tr->frameBuf.alloc(px * 4));
     CU(tr, PC_ERR_ALLOC, tr->scratch.alloc(px * 32));
-    tr->statusStride = (px + SHADE_BLOCK - 1) / SHADE_BLOCK + 1;
+    tr->statusStride = (px + 31) / 32 + 1;  // one status word per 32-ray tile
     CU(tr, PC_ERR_ALLOC, tr->status.alloc(tr->statusStride * MAX_BOUNCES * 8));
     tr->W = w;
     tr->H = h;

@@ -9,9 +9,9 @@
 //                   reference uses on GPUs, intersect.cl:353-575) or per-ray traversal
 //   k_shade         shadePrimaryRayMisses / shadeIndirectRayMisses + shadeHits
 //                   (pt_integrator.cl:17-275) with STABLE compaction of the occlusion and
-//                   indirect rays: warp ballot + popc prefix, block prefix in shared memory and a
-//                   single-pass decoupled look-back across blocks (ticket ordered), so ray order
-//                   == parent ray order, which is what makes bounce >= 1 reproducible
+//                   indirect rays: warp ballot + popc prefix inside a 32-ray tile and a single-pass
+//                   decoupled look-back across tiles (ticket ordered), so ray order == parent ray
+//                   order, which is what makes bounce >= 1 reproducible
 //   k_occlusion     rayIntersectionTest + accumulateEmissiveSamples (intersect.cl:26-180,
 //                   pt_integrator.cl:278-296)
 //   k_query         rayIntersectionQuery (intersect.cl:184-347) for the indirect rays
@@ -28,7 +28,10 @@ namespace pc {
 
 constexpr int MAX_BOUNCES = 32;
 constexpr int TRAV_BLOCK = 128;   // 4 warps
-constexpr int SHADE_BLOCK = 256;  // 8 warps
+constexpr int SHADE_BLOCK = 128;  // 4 warps
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 6
+#endif
 
 enum StatIdx {
     ST_QUERY_RAYS = 0, ST_OCCLUSION_RAYS, ST_NODES, ST_TRIS, ST_INSTANCES, ST_SHADED, ST_OCC_EMITTED,
@@ -337,7 +340,10 @@ __global__ void __launch_bounds__(TRAV_BLOCK) k_occlusion(DScene sc, const Ray *
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decoupled look-back over the shade blocks' (occlusion, indirect) totals.
+// Decoupled look-back over the shade TILES' (occlusion, indirect) totals.  A tile is the 32 rays a
+// warp shades at once; tiles are handed out by ticket, so tile t covers rays [32t, 32t+32) and every
+// predecessor of a tile is owned by a warp that is already running (or done): spinning on a
+// predecessor cannot deadlock, also when the grid is not fully resident.
 // status word: [63:62] 0 empty / 1 aggregate / 2 inclusive prefix, [61:31] occlusion, [30:0] indirect
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, uint32_t occ, uint32_t ind) {
@@ -357,7 +363,7 @@ __device__ __forceinline__ void lookback(volatile unsigned long long *status, ui
     int base = (int)ticket - 1;
     for (;;) {
         int idx = base - (int)lane;
-        unsigned long long v = pack_status(2ull, 0u, 0u);  // before block 0: an inclusive prefix of zero
+        unsigned long long v = pack_status(2ull, 0u, 0u);  // before tile 0: an inclusive prefix of zero
         if (idx >= 0) {
             do { v = status[idx]; } while ((v >> 62) == 0ull);
         }
@@ -378,103 +384,84 @@ __device__ __forceinline__ void lookback(volatile unsigned long long *status, ui
 }
 
 // shadePrimaryRayMisses / shadeIndirectRayMisses / shadeHits for rays[a][0 .. numRays[a]).
+// Persistent: every warp pulls 32-ray tiles by ticket until none are left; no block-wide barrier.
 template <bool COUNT>
-__global__ void __launch_bounds__(SHADE_BLOCK) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
+__global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                       unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
                                                       uint32_t minBouncesForRR, int a, int fixQ4) {
-    __shared__ uint32_t s_occ[SHADE_BLOCK / 32], s_ind[SHADE_BLOCK / 32];
-    __shared__ uint32_t s_ticket, s_occBase, s_indBase;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = lane_id();
     const uint32_t n = (uint32_t)ctl->numRays[a];
-    const uint32_t nBlocks = (n + SHADE_BLOCK - 1) / SHADE_BLOCK;
+    const uint32_t nTiles = (n + 31u) / 32u;
     if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // resources.go:230-238: both counters reset
         ctl->numRays[2] = 0;
         ctl->numRays[1 - a] = 0;
     }
-    if (blockIdx.x >= nBlocks) return;
-    // tickets are handed out in scheduling order, so every predecessor of a block is already
-    // resident (or done) when the block looks back: no deadlock under partial residency
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&ctl->ticket[bounce], 1u);
-    __syncthreads();
-    const uint32_t ticket = s_ticket;
-    const uint32_t i = ticket * SHADE_BLOCK + threadIdx.x;
     const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample + 1 + bounce];
-
-    ShadeOut so;
-    so.wantOcc = false; so.wantInd = false;
-    float pathIndexF = 0.0f;
     uint32_t shaded = 0;
-    if (i < n) {
-        const float4 rd = fb.rays[a][i].dir;
-        pathIndexF = rd.w;
-        const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
-        if (!fb.hitFlags[i]) {
-            if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
-                float3 kd = shadeMiss(sc, xyz(rd));
-                PathRec p = fb.paths[pathIndex];
-                float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
-                float4 c = fb.traceAcc[p.meta.x];
-                c.x += add.x; c.y += add.y; c.z += add.z;
-                fb.traceAcc[p.meta.x] = c;
-            }
-        } else {
-            shaded = 1;
-            const HitRec h = fb.hits[i];
-            const PathRec p = fb.paths[pathIndex];
-            shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, h.wuvt, h.meta.y, i, bounce, minBouncesForRR, randSeed, so);
-            if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
-            if (so.accum) {
-                const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
-                float4 c = fb.traceAcc[dst];
-                c.x += so.accumAdd.x; c.y += so.accumAdd.y; c.z += so.accumAdd.z;
-                fb.traceAcc[dst] = c;
-            }
-            if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
-        }
-    }
-    // ---- stable compaction (replaces the local/global atomics of pt_integrator.cl:162,176,188-197)
-    const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
-    const unsigned occMask = __ballot_sync(FULL, so.wantOcc), indMask = __ballot_sync(FULL, so.wantInd);
-    const unsigned ltMask = (1u << lane) - 1u;
-    uint32_t occOff = __popc(occMask & ltMask), indOff = __popc(indMask & ltMask);
-    if (lane == 0) {
-        s_occ[warp] = __popc(occMask);
-        s_ind[warp] = __popc(indMask);
-    }
-    __syncthreads();
-    uint32_t occTot = 0, indTot = 0;
-#pragma unroll
-    for (unsigned w = 0; w < SHADE_BLOCK / 32; w++) {
-        uint32_t oc = s_occ[w], ic = s_ind[w];
-        if (w < warp) { occOff += oc; indOff += ic; }
-        occTot += oc; indTot += ic;
-    }
-    if (warp == 0) {
-        uint32_t ob, ib;
-        lookback(status, ticket, occTot, indTot, ob, ib);
-        if (lane == 0) {
-            s_occBase = ob; s_indBase = ib;
-            if (ticket == nBlocks - 1) {  // last block publishes the queue lengths
-                ctl->numRays[2] = (int)(ob + occTot);
-                ctl->numRays[1 - a] = (int)(ib + indTot);
-                if (COUNT) {
-                    atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(ob + occTot));
-                    atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(ib + indTot));
+    for (;;) {
+        uint32_t ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&ctl->ticket[bounce], 1u);
+        ticket = __shfl_sync(FULL, ticket, 0);
+        if (ticket >= nTiles) break;
+        const uint32_t i = ticket * 32u + lane;
+        ShadeOut so;
+        so.wantOcc = false; so.wantInd = false;
+        float pathIndexF = 0.0f;
+        if (i < n) {
+            const float4 rd = fb.rays[a][i].dir;
+            pathIndexF = rd.w;
+            const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
+            if (!fb.hitFlags[i]) {
+                if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
+                    float3 kd = shadeMiss(sc, xyz(rd));
+                    PathRec p = fb.paths[pathIndex];
+                    float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
+                    float4 c = fb.traceAcc[p.meta.x];
+                    c.x += add.x; c.y += add.y; c.z += add.z;
+                    fb.traceAcc[p.meta.x] = c;
                 }
+            } else {
+                shaded++;
+                const HitRec h = fb.hits[i];
+                const PathRec p = fb.paths[pathIndex];
+                shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, h.wuvt, h.meta.y, i, bounce, minBouncesForRR, randSeed, so);
+                if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
+                if (so.accum) {
+                    const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
+                    float4 c = fb.traceAcc[dst];
+                    c.x += so.accumAdd.x; c.y += so.accumAdd.y; c.z += so.accumAdd.z;
+                    fb.traceAcc[dst] = c;
+                }
+                if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
             }
         }
-    }
-    __syncthreads();
-    if (so.wantOcc) {  // pt_integrator.cl:200-204
-        const uint32_t k = s_occBase + occOff;
-        fb.emissiveSamples[k] = f4(so.occSample, 0.0f);
-        fb.rays[2][k].origin = f4(so.occOrigin, so.occMaxDist);
-        fb.rays[2][k].dir = f4(so.occDir, pathIndexF);
-    }
-    if (so.wantInd) {  // :207-210
-        const uint32_t k = s_indBase + indOff;
-        fb.rays[1 - a][k].origin = f4(so.indOrigin, FLT_MAX);
-        fb.rays[1 - a][k].dir = f4(so.indDir, pathIndexF);
+        // ---- stable compaction (replaces the local/global atomics of pt_integrator.cl:162,176,188-197):
+        // ballot + popc inside the tile, decoupled look-back across tiles
+        const unsigned occMask = __ballot_sync(FULL, so.wantOcc), indMask = __ballot_sync(FULL, so.wantInd);
+        const unsigned ltMask = (1u << lane) - 1u;
+        const uint32_t occTot = __popc(occMask), indTot = __popc(indMask);
+        uint32_t occBase, indBase;
+        lookback(status, ticket, occTot, indTot, occBase, indBase);
+        if (ticket == nTiles - 1 && lane == 0) {  // the last tile publishes the queue lengths
+            ctl->numRays[2] = (int)(occBase + occTot);
+            ctl->numRays[1 - a] = (int)(indBase + indTot);
+            if (COUNT) {
+                atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(occBase + occTot));
+                atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(indBase + indTot));
+            }
+        }
+        if (so.wantOcc) {  // pt_integrator.cl:200-204
+            const uint32_t k = occBase + __popc(occMask & ltMask);
+            fb.emissiveSamples[k] = f4(so.occSample, 0.0f);
+            fb.rays[2][k].origin = f4(so.occOrigin, so.occMaxDist);
+            fb.rays[2][k].dir = f4(so.occDir, pathIndexF);
+        }
+        if (so.wantInd) {  // :207-210
+            const uint32_t k = indBase + __popc(indMask & ltMask);
+            fb.rays[1 - a][k].origin = f4(so.indOrigin, FLT_MAX);
+            fb.rays[1 - a][k].dir = f4(so.indDir, pathIndexF);
+        }
     }
     if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);
 }

@@ -18,9 +18,18 @@
 
 #ifdef __CUDACC__
 #define PC_HD __host__ __device__ __forceinline__
+// Out-of-line helpers (all arguments by value, so nothing is forced into local memory): they keep
+// k_shade's code footprint inside the instruction caches; inlining them at every call site made
+// the kernel 212 KB of SASS and the warps stalled on instruction fetch.
+#ifdef PC_INLINE_ALL
+#define PC_HD_NOINLINE __host__ __device__ __forceinline__
+#else
+#define PC_HD_NOINLINE __host__ __device__ __noinline__
+#endif
 #define PC_D __device__ __forceinline__
 #else
 #define PC_HD inline
+#define PC_HD_NOINLINE inline
 #endif
 
 #if defined(__CUDA_ARCH__)
