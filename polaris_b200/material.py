@@ -69,6 +69,11 @@ MATERIAL_NODE_DTYPE = np.dtype(
 assert MATERIAL_NODE_DTYPE.itemsize == 64  # optimized_scene.go:82-110
 
 
+def align4(value: int) -> int:
+    """compiler.go:556-563: next multiple of 4."""
+    return value + ((-value) % 4)
+
+
 class MaterialError(ValueError):
     pass
 
@@ -149,6 +154,15 @@ class _Parser:
                     val = ("tex", self.take("str")) if self.peek()[0] == "str" else ("float", self.take("num"))
                 else:
                     raise MaterialError(f"unknown bxdf parameter {pname!r}")
+                # BxdfParamNode.Validate (asset/material/node.go:138-163)
+                if val[0] == "vec3":
+                    comps = [float(c) for c in val[1]]
+                    if pname == "reflectance" and any(c >= 1.0 for c in comps):
+                        raise MaterialError(f"energy conservation violation for Parameter {pname!r}; ensure that all vector components are < 1.0")
+                    if pname in ("specularity", "transmittance") and any(c > 1.0 for c in comps):
+                        raise MaterialError(f"energy conservation violation for Parameter {pname!r}; ensure that all vector components are <= 1.0")
+                if pname == "roughness" and val[0] == "float" and float(val[1]) > 1.0:
+                    raise MaterialError(f"values for Parameter {pname!r} must be in the [0, 1] range")
                 e.params[pname] = val
                 if self.peek()[0] == ",":
                     self.i += 1
@@ -212,7 +226,7 @@ class MaterialCompiler:
         data = bytes(data)
         off = len(self.tex_data)
         self.tex_data += data
-        self.tex_data += b"\0" * ((-len(data)) % 4)  # align4 (compiler.go:528-537)
+        self.tex_data += b"\0" * (align4(len(data)) - len(data))  # compiler.go:528-537
         self.tex_meta.append((fmt, w, h, off))
         self.tex_index[name] = len(self.tex_meta) - 1
         return self.tex_index[name]

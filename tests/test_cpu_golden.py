@@ -1,0 +1,133 @@
+"""CPU tier: golden vectors generated from the reference's own kernels (tests/golden/make_golden.py)
+against (a) the oracle port and (b) the CUDA tracer's device functions compiled for the host
+(tests/emul, TEST ONLY -- the same pc_device.cuh / pc_layout.hpp the GPU runs: derived node64/tri48
+layout, nearest-first traversal with closest-hit culling and the reference-order tie-break, shading).
+
+Bars: bit-exact for RNG, hit flags, instance / triangle ids, barycentrics, distances, ray counters and
+tonemapped bytes; radiance bit-exact for the oracle, and for the emulated CUDA code too because both are
+built with -ffp-contract=off against the same libm (on the GPU itself the transcendental functions differ in
+the last ulp, so tests/test_gpu_parity.py uses the tolerances BASELINE.json states).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle.binding import OracleTracer
+from polaris_b200 import _lib
+from polaris_b200 import tracer as T
+
+from . import common as C
+from .golden.make_golden import CONFIGS, scene_digest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def scene_for(key, g):
+    w, h = CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    assert scene_digest(sc) == str(g["scene_sha256"]), \
+        f"the procedural scene {key} no longer matches the one the golden vectors were made from: regenerate tests/golden"
+    return sc, w, h
+
+
+def test_golden_rng_and_tonemap():
+    g = load("scalars")
+    out, final = OracleTracer().debug_rng(g["rng_states"], 8)
+    assert out.tobytes() == g["rng_out"].tobytes() and final.tobytes() == g["rng_final"].tobytes()
+    # first draw of state (0,0): x = 0 -> (871483, 234234) * 2^-32 (random_sampler.cl:10-15, by hand)
+    assert out[0, 0, 0] == np.float32(871483) * np.float32(1.0 / 4294967296.0)
+    assert out[0, 0, 1] == np.float32(234234) * np.float32(1.0 / 4294967296.0)
+    rgba = OracleTracer().debug_tonemap(g["tonemap_acc"], float(g["tonemap_weight"]), float(g["tonemap_exposure"]))
+    assert np.array_equal(rgba, g["tonemap_rgba"])
+    assert rgba[0].tolist() == [0, 0, 0, 255]  # black stays black, alpha is 255 (hdr.cl:22-27)
+    sc = C.small_scene("c1", 32, 32)
+    e = C.Emul(sc, 32, 32)
+    out = np.zeros((len(g["tonemap_acc"]), 4), np.uint8)
+    acc = np.ascontiguousarray(g["tonemap_acc"], np.float32)
+    e.lib.pe_tonemap(acc.ctypes.data, len(acc), float(g["tonemap_weight"]), float(g["tonemap_exposure"]), out.ctypes.data)
+    assert np.array_equal(out, g["tonemap_rgba"])
+    e.close()
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_golden_hit_records(key):
+    g = load(key)
+    sc, w, h = scene_for(key, g)
+    hit = g["flags"] == 1
+    orc = C.oracle_for(sc, w, h)
+    emu = C.Emul(sc, w, h)
+    cases = {"oracle": orc.debug_intersect(g["rays"], 0), "cuda per-ray (host build)": emu.intersect(g["rays"], 0)[:2],
+             "cuda reference-order (host build)": emu.intersect(g["rays"], 2)[:2]}
+    for label, (flags, hits) in cases.items():
+        assert np.array_equal(flags, g["flags"]), label
+        names = ("mesh_instance", "tri_index") if "mesh_instance" in hits.dtype.names else ("inst", "tri")
+        for mine, gold in zip(names, ("mesh_instance", "tri_index")):
+            assert np.array_equal(hits[mine][hit], g["hits"][gold][hit]), f"{label}: {gold}"
+        assert hits["wuvt"][hit].tobytes() == g["hits"]["wuvt"][hit].tobytes(), f"{label}: wuvt"
+    assert np.array_equal(orc.debug_intersect(g["occ_rays"], 1)[0], g["occ_flags"])
+    assert np.array_equal(emu.intersect(g["occ_rays"], 1)[0], g["occ_flags"])
+    assert np.array_equal(emu.intersect(g["occ_rays"], 3)[0], g["occ_flags"])
+    assert 0 < g["occ_flags"].sum() < len(g["occ_flags"])
+    emu.close()
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_golden_frames(key):
+    g = load(key)
+    sc, w, h = scene_for(key, g)
+    spp, seeds = int(g["spp"]), g["seeds"]
+    orc = C.oracle_for(sc, w, h)
+    r = T.make_block_request(w, h, spp=spp)
+    orc.trace(r, seeds)
+    assert C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h).tobytes() == g["full_acc"].tobytes()
+    assert np.array_equal(orc.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32), g["counters"])
+    st = orc.stats().device
+    assert (st["query_rays"], st["occlusion_rays"]) == (int(g["query_rays"]), int(g["occlusion_rays"]))
+    orc.merge_output(orc, r)
+    orc.sync_framebuffer(T.make_block_request(w, h, spp=spp))
+    assert np.array_equal(orc.frame_buffer, g["rgba"])
+    r0 = T.make_block_request(w, h, spp=1, num_bounces=1)
+    orc.trace(r0, seeds[:2])
+    assert orc.read_buffer(_lib.BUF_RAYS0, w * h, _lib.RAY_DTYPE).tobytes() == g["primary_rays"].tobytes()
+    assert C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h).tobytes() == g["bounce0_acc"].tobytes()
+    # the CUDA device code, host build: same frame
+    emu = C.Emul(sc, w, h)
+    emu.trace(T.make_block_request(w, h, spp=spp), seeds)
+    acc = emu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).reshape(-1, 4)[:, :3]
+    assert acc.tobytes() == g["full_acc"].tobytes()
+    assert np.array_equal(emu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32), g["counters"])
+    emu.close()
+
+
+@pytest.mark.parametrize("key", ["c2", "c4"])
+def test_golden_bxdf_tables(key):
+    g = load("bxdf_" + key)
+    w, h = CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    assert scene_digest(sc) == str(g["scene_sha256"])
+    o = C.oracle_for(sc, w, h).debug_bxdf(g["records"])
+    emu = C.Emul(sc, w, h)
+    e = emu.bxdf(g["records"])
+    for f in ("sample", "sample_pdf", "dir", "pdf", "eval"):
+        assert o[f].tobytes() == g["out"][f].tobytes(), f"oracle {f}"
+        assert e[f].tobytes() == g["out"][f].tobytes(), f"cuda host build {f}"
+    emu.close()
+
+
+def test_derived_layout_properties():
+    """pc_layout.hpp: the 16-byte aligned traversal layout derived at upload from the reference buffers."""
+    for key in ("c1", "c2", "c3", "c4"):
+        w, h = CONFIGS[key]
+        sc = C.small_scene(key, w, h)
+        emu = C.Emul(sc, w, h)
+        info = emu.layout_info()
+        n = sc.bvh_nodes
+        assert info["inner_nodes"] == int((n["ldata"] > 0).sum())
+        assert info["top_depth"] >= 0 and info["mesh_depth"] >= 0 and info["stack_need"] >= 1
+        assert info["stack_need"] <= 64  # PC_STACK_SIZE; deeper scenes are refused with PC_ERR_STACK_DEPTH
+        emu.close()
