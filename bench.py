@@ -341,6 +341,7 @@ def run_cuda_multi(args):
     import torch.distributed as dist
 
     from polaris_b200 import tracer as T
+    from polaris_b200.gather import gather_rows_to_primary
     from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -379,23 +380,15 @@ def run_cuda_multi(args):
         # exchange step: block rows -> rank 0 over NCCL (NVLink), added into the frame accumulator
         ptr, nbytes = tr.trace_rows(req)
         mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
+        blocks = gather_rows_to_primary(mine, rows, w, rank, world, recv)
         if rank == 0:
             tr.merge_output(tr, req)
-            reqs = []
-            off = 0
+            torch.cuda.synchronize()  # the received rows are complete before pc_merge_rows reads them on its own stream
             for r in range(1, world):
-                n = w * int(rows[r]) * 4
-                reqs.append((r, off, n, dist.irecv(recv[off:off + n], src=r)))
-                off += n
-            for r, off, n, work in reqs:
-                work.wait()
-                torch.cuda.synchronize()
                 rr = T.make_block_request(w, h, block_y=int(sum(rows[:r])), block_h=int(rows[r]), spp=pass_spp,
                                           accumulated_samples=acc_samples + pass_spp)
-                tr.merge_rows(recv[off:off + n].data_ptr(), True, rr)
+                tr.merge_rows(blocks[r].data_ptr(), True, rr)
             tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc_samples), want_pixels=e2e)
-        else:
-            dist.send(mine, dst=0)
         # feedback for the perfect scheduler (scheduler.go:50-80): rows and render time of every tracer
         t = torch.tensor([float(rows[rank]), t_trace, float(d["query_rays"] + d["occlusion_rays"]), float(d["kernel_launches"])],
                          dtype=torch.float64, device="cuda")

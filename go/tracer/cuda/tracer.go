@@ -1,0 +1,370 @@
+// Package cuda implements polaris's tracer.Tracer interface (tracer/tracer.go:80-111) over
+// libpolaris_cuda.so, the B200 (sm_100a) path-tracing backend.  It is the cgo counterpart of
+// tracer/opencl: renderer/default.go, renderer/opengl.go, the block schedulers of
+// tracer/scheduler.go and the `polaris render` commands drive it unchanged once
+// renderer.initTracers constructs these tracers instead of opencl ones (see INTEGRATION.md).
+//
+// NOTE: written against include/polaris_cuda.h without a Go toolchain in the build image; the
+// same call sequence is exercised through ctypes by polaris_b200/tracer.py and the test suite.
+package cuda
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../../include
+#cgo LDFLAGS: -lpolaris_cuda
+#include <stdlib.h>
+#include "polaris_cuda.h"
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"math/rand"
+	"sync"
+	"time"
+	"unsafe"
+
+	"github.com/achilleasa/polaris/asset/scene"
+	"github.com/achilleasa/polaris/tracer"
+)
+
+// Errors mirror tracer/opencl/errors.go so callers can keep comparing against sentinel values.
+var (
+	ErrNoDevice              = errors.New("cuda tracer: no usable CUDA device")
+	ErrAllocatingBuffer      = errors.New("cuda tracer: could not allocate device buffer")
+	ErrCopyingDataToHost     = errors.New("cuda tracer: could not copy device data to host buffer")
+	ErrCopyingDataToDevice   = errors.New("cuda tracer: could not copy host data to device buffer")
+	ErrKernelExecutionFailed = errors.New("cuda tracer: kernel execution failed")
+	ErrUnsupportedChangeType = errors.New("cuda tracer: unsupported change type")
+	ErrInvalidChangeData     = errors.New("cuda tracer: invalid data type for change")
+	ErrNoSceneData           = errors.New("cuda tracer: no scene data uploaded")
+)
+
+// DeviceInfo is what `polaris list-devices` prints per device (cmd/list_devices.go:13-38).
+type DeviceInfo struct {
+	Ordinal  int
+	Name     string
+	SMs      uint32
+	ClockMHz uint32
+	Speed    uint32 // SMs*MHz/1000, the unit of tracer/opencl/device/device.go:209-222
+}
+
+// Devices enumerates the CUDA devices the library can drive.
+func Devices() []DeviceInfo {
+	n := int(C.pc_device_count())
+	out := make([]DeviceInfo, 0, n)
+	for i := 0; i < n; i++ {
+		var name [256]C.char
+		var sm, mhz, speed C.uint32_t
+		if C.pc_device_info(C.int(i), &name[0], 256, &sm, &mhz, &speed) != 0 {
+			continue
+		}
+		out = append(out, DeviceInfo{i, C.GoString(&name[0]), uint32(sm), uint32(mhz), uint32(speed)})
+	}
+	return out
+}
+
+// Tracer is one CUDA device behind the tracer.Tracer interface.
+type Tracer struct {
+	sync.Mutex
+	id      string
+	ordinal int
+	handle  *C.pc_tracer
+	stats   *tracer.Stats
+
+	// queued state changes, applied by the next Trace (tracer/opencl/tracer.go:150-158,198)
+	changeBuffer map[tracer.ChangeType]interface{}
+	hasScene     bool
+
+	// Seeds, when non-nil, supplies the host seed list (1 camera seed + NumBounces shade seeds per
+	// sample, in the order tracer.go:222 / pipeline.go:146 draw them); nil draws from math/rand like
+	// the reference.
+	Seeds func(n int) []uint32
+
+	frameBuffer []byte
+}
+
+// NewTracer mirrors opencl.NewTracer (tracer/opencl/tracer.go:58-73).
+func NewTracer(id string, ordinal int) (*Tracer, error) {
+	return &Tracer{
+		id:           id,
+		ordinal:      ordinal,
+		stats:        &tracer.Stats{},
+		changeBuffer: make(map[tracer.ChangeType]interface{}),
+	}, nil
+}
+
+func (tr *Tracer) lastError(code C.int) error {
+	msg := "unknown error"
+	if m := C.pc_last_error(tr.handle); m != nil {
+		msg = C.GoString(m)
+	}
+	var base error
+	switch code {
+	case C.PC_ERR_NO_DEVICE:
+		base = ErrNoDevice
+	case C.PC_ERR_ALLOC:
+		base = ErrAllocatingBuffer
+	case C.PC_ERR_COPY_TO_DEVICE:
+		base = ErrCopyingDataToDevice
+	case C.PC_ERR_COPY_TO_HOST:
+		base = ErrCopyingDataToHost
+	case C.PC_ERR_KERNEL:
+		base = ErrKernelExecutionFailed
+	case C.PC_ERR_NO_SCENE_DATA:
+		return ErrNoSceneData
+	default:
+		return fmt.Errorf("cuda tracer: %s (code %d)", msg, int(code))
+	}
+	return fmt.Errorf("%w: %s", base, msg)
+}
+
+// Id, Flags, Speed: tracer/opencl/tracer.go:75-92.
+func (tr *Tracer) Id() string         { return tr.id }
+func (tr *Tracer) Flags() tracer.Flag { return tracer.Local }
+func (tr *Tracer) Speed() uint32 {
+	if tr.handle == nil {
+		for _, d := range Devices() {
+			if d.Ordinal == tr.ordinal {
+				return d.Speed
+			}
+		}
+		return 0
+	}
+	return uint32(C.pc_speed(tr.handle))
+}
+
+// Init: tracer/opencl/tracer.go:95-117.
+func (tr *Tracer) Init() error {
+	tr.Lock()
+	defer tr.Unlock()
+	if tr.handle != nil {
+		return nil
+	}
+	cid := C.CString(tr.id)
+	defer C.free(unsafe.Pointer(cid))
+	if rc := C.pc_create(C.int(tr.ordinal), cid, &tr.handle); rc != 0 {
+		msg := ""
+		if m := C.pc_last_error(nil); m != nil {
+			msg = C.GoString(m)
+		}
+		return fmt.Errorf("%w: %s", ErrNoDevice, msg)
+	}
+	return nil
+}
+
+// Close: tracer/opencl/tracer.go:120-142 (idempotent).
+func (tr *Tracer) Close() {
+	tr.Lock()
+	defer tr.Unlock()
+	if tr.handle != nil {
+		C.pc_destroy(tr.handle)
+		tr.handle = nil
+	}
+	tr.hasScene = false
+}
+
+func (tr *Tracer) Stats() *tracer.Stats { return tr.stats }
+
+// UpdateState: tracer/opencl/tracer.go:150-158.
+func (tr *Tracer) UpdateState(mode tracer.UpdateMode, changeType tracer.ChangeType, data interface{}) (time.Duration, error) {
+	tr.Lock()
+	defer tr.Unlock()
+	tr.changeBuffer[changeType] = data
+	if mode == tracer.Synchronous {
+		return tr.commitChanges()
+	}
+	return 0, nil
+}
+
+// commitChanges: tracer/opencl/tracer.go:161-191.  The library copies every buffer during the
+// call and never retains a Go pointer (cgo pointer-passing rules).
+func (tr *Tracer) commitChanges() (time.Duration, error) {
+	if len(tr.changeBuffer) == 0 {
+		return 0, nil
+	}
+	start := time.Now()
+	for changeType, data := range tr.changeBuffer {
+		switch changeType {
+		case tracer.FrameDimensions:
+			dims, ok := data.([2]uint32)
+			if !ok {
+				return time.Since(start), ErrInvalidChangeData
+			}
+			if rc := C.pc_resize(tr.handle, C.uint32_t(dims[0]), C.uint32_t(dims[1])); rc != 0 {
+				return time.Since(start), tr.lastError(rc)
+			}
+			tr.frameBuffer = make([]byte, int(dims[0])*int(dims[1])*4)
+		case tracer.SceneData:
+			sc, ok := data.(*scene.Scene)
+			if !ok {
+				return time.Since(start), ErrInvalidChangeData
+			}
+			if err := tr.uploadScene(sc); err != nil {
+				return time.Since(start), err
+			}
+		case tracer.CameraData:
+			cam, ok := data.(*scene.Camera)
+			if !ok {
+				return time.Since(start), ErrInvalidChangeData
+			}
+			eye := [3]C.float{C.float(cam.Position[0]), C.float(cam.Position[1]), C.float(cam.Position[2])}
+			var fr [16]C.float
+			for k := 0; k < 4; k++ {
+				for c := 0; c < 4; c++ {
+					fr[4*k+c] = C.float(cam.Frustrum[k][c])
+				}
+			}
+			if rc := C.pc_set_camera(tr.handle, &eye[0], &fr[0]); rc != 0 {
+				return time.Since(start), tr.lastError(rc)
+			}
+		default:
+			return time.Since(start), fmt.Errorf("%w %d", ErrUnsupportedChangeType, changeType)
+		}
+	}
+	tr.changeBuffer = make(map[tracer.ChangeType]interface{})
+	tr.stats.UpdateTime = time.Since(start)
+	return tr.stats.UpdateTime, nil
+}
+
+func sliceView(ptr unsafe.Pointer, n int, elem uintptr) (unsafe.Pointer, C.uint64_t) {
+	if n == 0 {
+		return nil, 0
+	}
+	return ptr, C.uint64_t(uintptr(n) * elem)
+}
+
+// uploadScene: bufferSet.UploadSceneData (tracer/opencl/buffers.go:177-201); struct sizes are the
+// ones asset/scene/optimized_scene.go documents (32/80/64/80/16 bytes).
+func (tr *Tracer) uploadScene(sc *scene.Scene) error {
+	var v C.pc_scene_view
+	if len(sc.BvhNodeList) > 0 {
+		v.bvh_nodes, v.bvh_nodes_bytes = sliceView(unsafe.Pointer(&sc.BvhNodeList[0]), len(sc.BvhNodeList), unsafe.Sizeof(sc.BvhNodeList[0]))
+	}
+	if len(sc.MeshInstanceList) > 0 {
+		v.mesh_instances, v.mesh_instances_bytes = sliceView(unsafe.Pointer(&sc.MeshInstanceList[0]), len(sc.MeshInstanceList), unsafe.Sizeof(sc.MeshInstanceList[0]))
+	}
+	if len(sc.MaterialNodeList) > 0 {
+		v.material_nodes, v.material_nodes_bytes = sliceView(unsafe.Pointer(&sc.MaterialNodeList[0]), len(sc.MaterialNodeList), unsafe.Sizeof(sc.MaterialNodeList[0]))
+	}
+	if len(sc.TextureData) > 0 {
+		v.texture_data, v.texture_data_bytes = sliceView(unsafe.Pointer(&sc.TextureData[0]), len(sc.TextureData), 1)
+	}
+	if len(sc.TextureMetadata) > 0 {
+		v.texture_metadata, v.texture_metadata_bytes = sliceView(unsafe.Pointer(&sc.TextureMetadata[0]), len(sc.TextureMetadata), unsafe.Sizeof(sc.TextureMetadata[0]))
+	}
+	if len(sc.VertexList) > 0 {
+		v.vertices, v.vertices_bytes = sliceView(unsafe.Pointer(&sc.VertexList[0]), len(sc.VertexList), unsafe.Sizeof(sc.VertexList[0]))
+	}
+	if len(sc.NormalList) > 0 {
+		v.normals, v.normals_bytes = sliceView(unsafe.Pointer(&sc.NormalList[0]), len(sc.NormalList), unsafe.Sizeof(sc.NormalList[0]))
+	}
+	if len(sc.UvList) > 0 {
+		v.uvs, v.uvs_bytes = sliceView(unsafe.Pointer(&sc.UvList[0]), len(sc.UvList), unsafe.Sizeof(sc.UvList[0]))
+	}
+	if len(sc.MaterialIndex) > 0 {
+		v.material_indices, v.material_indices_bytes = sliceView(unsafe.Pointer(&sc.MaterialIndex[0]), len(sc.MaterialIndex), 4)
+	}
+	if len(sc.EmissivePrimitives) > 0 {
+		v.emissives, v.emissives_bytes = sliceView(unsafe.Pointer(&sc.EmissivePrimitives[0]), len(sc.EmissivePrimitives), unsafe.Sizeof(sc.EmissivePrimitives[0]))
+	}
+	v.scene_diffuse_mat_index = C.int32_t(sc.SceneDiffuseMatIndex)
+	v.scene_emissive_mat_index = C.int32_t(sc.SceneEmissiveMatIndex)
+	if rc := C.pc_upload_scene(tr.handle, &v); rc != 0 {
+		return tr.lastError(rc)
+	}
+	tr.hasScene = true
+	return nil
+}
+
+func toC(r *tracer.BlockRequest) C.pc_block_request {
+	return C.pc_block_request{
+		frame_w: C.uint32_t(r.FrameW), frame_h: C.uint32_t(r.FrameH),
+		block_x: C.uint32_t(r.BlockX), block_y: C.uint32_t(r.BlockY),
+		block_w: C.uint32_t(r.BlockW), block_h: C.uint32_t(r.BlockH),
+		samples_per_pixel: C.uint32_t(r.SamplesPerPixel), num_bounces: C.uint32_t(r.NumBounces),
+		min_bounces_for_rr: C.uint32_t(r.MinBouncesForRR), exposure: C.float(r.Exposure),
+		seed: C.uint32_t(r.Seed), accumulated_samples: C.uint32_t(r.AccumulatedSamples),
+	}
+}
+
+// Trace: tracer/opencl/tracer.go:194-247.  Seed and AccumulatedSamples are updated in place like
+// the reference does.
+func (tr *Tracer) Trace(blockReq *tracer.BlockRequest) (time.Duration, error) {
+	tr.Lock()
+	defer tr.Unlock()
+	start := time.Now()
+	if _, err := tr.commitChanges(); err != nil {
+		return time.Since(start), err
+	}
+	if !tr.hasScene {
+		return time.Since(start), ErrNoSceneData
+	}
+	n := int(blockReq.SamplesPerPixel) * (1 + int(blockReq.NumBounces))
+	var seeds []uint32
+	if tr.Seeds != nil {
+		seeds = tr.Seeds(n)
+	} else {
+		seeds = make([]uint32, n)
+		for i := range seeds {
+			seeds[i] = rand.Uint32() // tracer.go:222, pipeline.go:146
+		}
+	}
+	req := toC(blockReq)
+	var st C.pc_stats
+	var sp *C.uint32_t
+	if n > 0 {
+		sp = (*C.uint32_t)(unsafe.Pointer(&seeds[0]))
+	}
+	if rc := C.pc_trace(tr.handle, &req, sp, C.size_t(n), &st); rc != 0 {
+		return time.Since(start), tr.lastError(rc)
+	}
+	blockReq.Seed = uint32(req.seed)
+	blockReq.AccumulatedSamples = uint32(req.accumulated_samples)
+	tr.stats.BlockW = blockReq.BlockW
+	tr.stats.BlockH = blockReq.BlockH
+	tr.stats.RenderTime = time.Since(start)
+	return tr.stats.RenderTime, nil
+}
+
+// MergeOutput: tracer/opencl/tracer.go:279-286.  Called concurrently on the primary by every worker
+// goroutine (renderer/default.go:191); the library serialises per destination and returns without
+// waiting for the add, SyncFramebuffer is the fence.
+func (tr *Tracer) MergeOutput(other tracer.Tracer, blockReq *tracer.BlockRequest) (time.Duration, error) {
+	start := time.Now()
+	src, ok := other.(*Tracer)
+	if !ok {
+		return 0, fmt.Errorf("merge failed: unsupported tracer instance") // tracer.go:282
+	}
+	req := toC(blockReq)
+	if rc := C.pc_merge_output(tr.handle, src.handle, &req); rc != 0 {
+		return time.Since(start), tr.lastError(rc)
+	}
+	return time.Since(start), nil
+}
+
+// SyncFramebuffer: tracer/opencl/tracer.go:250-276.  The tonemapped RGBA8 frame is what the
+// reference's SaveFrameBuffer / CopyFrameBufferToOpenGLTexture post-process stages read
+// (pipeline.go:216-256); it is returned by FrameBuffer().
+func (tr *Tracer) SyncFramebuffer(blockReq *tracer.BlockRequest) (time.Duration, error) {
+	tr.Lock()
+	defer tr.Unlock()
+	start := time.Now()
+	if !tr.hasScene {
+		return 0, ErrNoSceneData
+	}
+	req := toC(blockReq)
+	var out *C.uint8_t
+	if len(tr.frameBuffer) > 0 {
+		out = (*C.uint8_t)(unsafe.Pointer(&tr.frameBuffer[0]))
+	}
+	if rc := C.pc_sync_framebuffer(tr.handle, &req, out); rc != 0 {
+		return time.Since(start), tr.lastError(rc)
+	}
+	return time.Since(start), nil
+}
+
+// FrameBuffer returns the RGBA8 pixels of the last SyncFramebuffer (FrameW*FrameH*4 bytes).
+func (tr *Tracer) FrameBuffer() []byte { return tr.frameBuffer }
+
+var _ tracer.Tracer = (*Tracer)(nil)

@@ -274,3 +274,75 @@ def test_c2_full_size_one_sample():
     assert st["query_rays"] >= w * h
     assert np.isfinite(g).all() and (g >= 0).all()
     cu.close()
+
+
+# --------------------------------------------------------------------------------------------
+# Golden vectors produced by the reference's own kernels (tests/golden/make_golden.py): the GPU box has
+# neither /root/reference nor necessarily oracle/_ref, the committed fixtures travel.
+import os  # noqa: E402
+
+from .golden.make_golden import CONFIGS as GOLDEN_CONFIGS  # noqa: E402
+from .golden.make_golden import scene_digest  # noqa: E402
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_golden_hits_and_frames(key):
+    g = np.load(os.path.join(_GOLDEN, key + ".npz"))
+    w, h = GOLDEN_CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    assert scene_digest(sc) == str(g["scene_sha256"])
+    cu = C.cuda_for(sc, w, h)
+    hit = g["flags"] == 1
+    for label, mode, ref_order in (("per-ray", 0, 0), ("packet", 2, 0), ("reference-order", 0, 1)):
+        cu.set_option(_lib.OPT_REFERENCE_ORDER, ref_order)
+        gf, gh = cu.debug_intersect(g["rays"], mode)
+        assert np.array_equal(gf, g["flags"]), label
+        assert np.array_equal(gh["mesh_instance"][hit], g["hits"]["mesh_instance"][hit]), label
+        assert np.array_equal(gh["tri_index"][hit], g["hits"]["tri_index"][hit]), label
+        assert gh["wuvt"][hit].tobytes() == g["hits"]["wuvt"][hit].tobytes(), label
+    cu.set_option(_lib.OPT_REFERENCE_ORDER, 0)
+    assert np.array_equal(cu.debug_intersect(g["occ_rays"], 1)[0], g["occ_flags"])
+    spp, seeds = int(g["spp"]), g["seeds"]
+    r = T.make_block_request(w, h, spp=spp)
+    cu.trace(r, seeds)
+    _assert_close_pixels(C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h), g["full_acc"], 1e-3, f"golden {key} full depth")
+    st = cu.stats().device
+    assert abs(st["query_rays"] - int(g["query_rays"])) <= 4 and abs(st["occlusion_rays"] - int(g["occlusion_rays"])) <= 4
+    cu.merge_output(cu, r)
+    cu.sync_framebuffer(T.make_block_request(w, h, spp=spp))
+    d = np.abs(cu.frame_buffer.astype(int) - g["rgba"].astype(int))
+    assert (d > 1).sum() <= 2, f"{(d > 1).sum()} bytes of the tonemapped frame differ by more than 1 LSB"
+    cu.trace(T.make_block_request(w, h, spp=1, num_bounces=1), seeds[:2])
+    assert cu.read_buffer(_lib.BUF_RAYS0, w * h, _lib.RAY_DTYPE).tobytes() == g["primary_rays"].tobytes()
+    _assert_close_pixels(C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h), g["bounce0_acc"], 1e-4, f"golden {key} bounce 0")
+    cu.close()
+
+
+def test_golden_scalars():
+    g = np.load(os.path.join(_GOLDEN, "scalars.npz"))
+    sc = C.small_scene("c1", 32, 32)
+    cu = C.cuda_for(sc, 32, 32)
+    out, final = cu.debug_rng(g["rng_states"], 8)
+    assert out.tobytes() == g["rng_out"].tobytes() and final.tobytes() == g["rng_final"].tobytes()
+    rgba = cu.debug_tonemap(g["tonemap_acc"], float(g["tonemap_weight"]), float(g["tonemap_exposure"]))
+    assert np.abs(rgba.astype(int) - g["tonemap_rgba"].astype(int)).max() <= 1
+    cu.close()
+
+
+@pytest.mark.parametrize("key", ["c2", "c4"])
+def test_golden_bxdf_tables(key):
+    g = np.load(os.path.join(_GOLDEN, f"bxdf_{key}.npz"))
+    w, h = GOLDEN_CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    assert scene_digest(sc) == str(g["scene_sha256"])
+    cu = C.cuda_for(sc, w, h)
+    got = cu.debug_bxdf(g["records"])
+    for f in ("sample", "sample_pdf", "dir", "pdf", "eval"):
+        a, b = np.atleast_2d(got[f].T).T.astype(np.float64), np.atleast_2d(g["out"][f].T).T.astype(np.float64)
+        assert (np.isfinite(a) == np.isfinite(b)).all(), f
+        fin = np.isfinite(a) & np.isfinite(b)
+        err = np.abs(a - b)[fin] / np.maximum(np.abs(b)[fin], 1e-3)
+        assert float((err > 1e-4).mean()) <= 2e-3, f
+    cu.close()
