@@ -162,8 +162,9 @@ def cpu_trace_sample(sc, w, h, spp, config_number, rows=None):
     dt = time.perf_counter() - t0
     d = tr.stats().device
     rays = d["query_rays"] + d["occlusion_rays"]
+    cores = tr.threads() if hasattr(tr, "threads") else (os.cpu_count() or 1)
     tr.close()
-    return rays / dt / 1e6, (os.cpu_count() or 1), kind, dt, rays
+    return rays / dt / 1e6, cores, kind, dt, rays
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,13 +199,26 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
-def workload_config(n, w, h, spp):
+WORKLOADS = {
+    "c1": "configs[0]: procedurally generated diffuse sphere, 512x512, 128 spp",
+    "c2": "configs[1]: synthetic Cornell box, layered diffuse/conductor/dielectric materials, 1024x1024, 256 spp",
+    "c3": "configs[2]: mesh-instancing stress, 1,000 instances of a 100k-triangle procedural mesh, 1920x1080, 64 spp",
+    "c4": "configs[3]: 10M-triangle displaced terrain, roughDielectric + dispersion, synthetic HDR textures, 3840x2160, 64 spp",
+    "c5": "configs[4] on ONE GPU: 3840x2160 layered Cornell box, one 64-spp pass of the 1024-spp job",
+}
+
+
+def workload_config(n, w, h, spp, config="c2", sc=None):
     if n == 1:
-        wl = "configs[1]: synthetic Cornell box, layered diffuse/conductor/dielectric materials, 1024x1024, 256 spp"
+        wl = WORKLOADS[config]
+        if sc is not None and config != "c2":
+            return {"workload": wl, "frame": [w, h], "spp": spp, "num_bounces": NUM_BOUNCES, "min_bounces_for_rr": MIN_RR,
+                    "triangles": int(sc.num_triangles), "instances": int(len(sc.mesh_instances)), "scene_bytes": int(sc.nbytes()),
+                    "l2": "per-step ray/path state (220 B/px x frame, re-written every bounce) exceeds the 126 MB L2"}
     else:
         wl = f"configs[4]: 3840x2160 layered Cornell box, 1024 spp in 64-spp passes, rows split over {n} GPUs by the perfect scheduler"
     return {"workload": wl, "frame": [w, h], "spp": spp, "num_bounces": NUM_BOUNCES, "min_bounces_for_rr": MIN_RR,
@@ -219,14 +233,22 @@ def run_cuda_single(args):
     from polaris_b200 import tracer as T
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
-    w, h, spp, cfgno = 1024, 1024, args.spp or 256, 2
-    sc = build_scene("c2_cornell", w, h)
+    from polaris_b200 import scenes
+
+    cfg_name = {"c1": "c1_sphere", "c2": "c2_cornell", "c3": "c3_instancing", "c4": "c4_terrain", "c5": "c5_cornell_4k"}[args.config]
+    w, h, cfg_spp = scenes.CONFIGS[cfg_name]
+    spp, cfgno = args.spp or cfg_spp, int(args.config[1])
+    if args.config == "c5":
+        spp = args.spp or 64  # one 64-spp pass of the 1024-spp job (what a rank does per step at N > 1)
+    sc = build_scene(cfg_name, w, h)
     seeds = T.splitmix_seeds(cfgno, spp * (1 + NUM_BOUNCES))
     tr = T.CudaTracer("cuda:0", 0)
     tr.init()
     tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
     tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+    if args.chains:
+        tr.set_option(_lib.OPT_SAMPLE_CHAINS, args.chains)
 
     def frame(e2e=False):
         if e2e:  # host scene buffers -> device, every step
@@ -311,20 +333,21 @@ def run_cuda_single(args):
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if not args.no_cpu:
-        v, cores, kind, cdt, crays = cpu_trace_sample(sc, w, h, args.cpu_spp, cfgno)
+        cpu_rows = h if w * h <= 1024 * 1024 else max(16, (1024 * 1024) // w)  # bound the sample on the big frames
+        v, cores, kind, cdt, crays = cpu_trace_sample(sc, w, h, args.cpu_spp, cfgno, cpu_rows)
         cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind,
-               "sample": f"{w}x{h}, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
+               "sample": f"{w}x{cpu_rows} rows of the {w}x{h} frame, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
         log(f"[bench] cpu baseline ({kind}, {cores} cores): {v:.2f} Mrays/s")
 
     line = {
         "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp, args.config, sc),
         "spp_mpix_per_s": w * h * spp * args.steps / dt / 1e6, "gpu_launches": int(tot_launch), "clocks": clk,
         "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roofline, "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -355,6 +378,9 @@ def run_cuda_multi(args):
     sc = objs[0]
     tr = T.CudaTracer(f"cuda:{local}", local)
     tr.init()
+    if args.chains:
+        from polaris_b200 import _lib
+        tr.set_option(_lib.OPT_SAMPLE_CHAINS, args.chains)
     tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
     tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
@@ -377,6 +403,7 @@ def run_cuda_multi(args):
         tr.trace(req, seeds)
         t_trace = time.perf_counter() - t0
         d = tr.stats().device
+        t1 = time.perf_counter()
         # exchange step: block rows -> rank 0 over NCCL (NVLink), added into the frame accumulator
         ptr, nbytes = tr.trace_rows(req)
         mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
@@ -389,6 +416,7 @@ def run_cuda_multi(args):
                                           accumulated_samples=acc_samples + pass_spp)
                 tr.merge_rows(blocks[r].data_ptr(), True, rr)
             tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc_samples), want_pixels=e2e)
+        t2 = time.perf_counter()
         # feedback for the perfect scheduler (scheduler.go:50-80): rows and render time of every tracer
         t = torch.tensor([float(rows[rank]), t_trace, float(d["query_rays"] + d["occlusion_rays"]), float(d["kernel_launches"])],
                          dtype=torch.float64, device="cuda")
@@ -397,6 +425,9 @@ def run_cuda_multi(args):
         for r in range(world):
             speeds[r].set_stats(int(allt[r][0].item()), float(allt[r][1].item()))
         acc_samples += pass_spp
+        if rank == 0 and args.verbose:
+            log(f"[bench] step: rows {[int(x[0].item()) for x in allt]} trace ms {[round(x[1].item() * 1e3, 1) for x in allt]} "
+                f"device ms(rank0) {d['device_time_ns'] / 1e6:.1f} gather+merge+tonemap {1e3 * (t2 - t1):.1f} ms, stats exchange {1e3 * (time.perf_counter() - t2):.1f} ms")
         return sum(float(x[2].item()) for x in allt), sum(float(x[3].item()) for x in allt)
 
     for i in range(args.warmup):
@@ -443,13 +474,32 @@ def run_cuda_multi(args):
                     "h2d_bytes_per_step": int((sc.nbytes() + seeds.nbytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
             "roofline": None, "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     tr.close()
     dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """Print the ONE JSON line on the real stdout (see main(): fd 1 is pointed at stderr while we run)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL / torch / CUDA libraries occasionally write to fd 1 (e.g. "NCCL version ..."): keep fd 1 for the JSON
+    # line only by routing everything else to stderr at the file-descriptor level.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -458,6 +508,10 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per step (debugging only; invalidates the config)")
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
+    ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="N=1 only: BASELINE config to run (default c2 = configs[1], the one the metric is quoted on)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

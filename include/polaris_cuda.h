@@ -133,8 +133,15 @@ typedef enum pc_option {
     PC_OPT_USE_GRAPH = 3,       /* 1 (default): replay one CUDA graph per sample          */
     PC_OPT_FIX_Q4 = 4,          /* 1 (default): emissive hits accumulate at pixelIndex;
                                    0: at the ray's path index like pt_integrator.cl:106   */
-    PC_OPT_KERNEL_TIMERS = 5    /* 1: direct launches bracketed by CUDA events on the handle's
-                                   stream, per-class times in pc_stats (measurement mode)   */
+    PC_OPT_KERNEL_TIMERS = 5,   /* 1: direct launches bracketed by CUDA events on the handle's
+                                   stream, per-class times in pc_stats (measurement mode;
+                                   implies one sample chain)                                */
+    PC_OPT_SAMPLE_CHAINS = 6    /* 1..8 (default 4): independent sample chains in flight.  Chain c
+                                   traces samples c, c+n, ... with its own ray/path/hit state on its
+                                   own stream so the launches of different samples overlap; chains
+                                   > 0 accumulate separately and are added in chain order at the
+                                   end of pc_trace (deterministic; differs from 1 chain only in
+                                   float summation order)                                   */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */

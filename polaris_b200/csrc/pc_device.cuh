@@ -699,106 +699,157 @@ struct TravStats {
 // of t plus the reference-order key -- never by the rounding of the box test.
 #define PC_CULL_SLACK 1.0001f
 
-// One stack-based traversal of the derived layout.
+// Stack-based traversal of the derived layout, written as a per-ray state machine so that the same
+// three steps serve the plain loop below (host build / tests) and the persistent kernels, which
+// interleave them with warp-level refilling of finished lanes (pc_kernels.cuh).
 //   ANY_HIT == false : rayIntersectionQuery semantics (intersect.cl:184-347) -- closest hit; the
 //                      result equals the reference's left-first walk because ties on t go to the
 //                      smaller (instance dfsRank, triangle index), the order that walk visits.
 //   ANY_HIT == true  : rayIntersectionTest semantics (:26-180) -- same cull predicate as the
 //                      reference (entry >= ray tmax), so the boolean is identical in any order.
-// Children are visited nearest first.  Returns 1 on hit.
+// Children are visited nearest first.
+struct Trav {
+    float3 o0, d0;      // the ray as given (world space)
+    float3 o, d, invDir;  // the ray in the current (world or mesh) space
+    float tmaxRay;
+    uint32_t curInst, curRank;
+    uint32_t cur;       // current reference; REF_DONE when the walk is over
+    int sp;
+    Hit best;
+};
+
+PC_HD void travInit(Trav &t, const DScene &sc, float3 o0, float3 d0, float tmaxRay) {
+    t.o0 = o0; t.d0 = d0; t.o = o0; t.d = d0;
+    t.invDir = f3(1.0f / d0.x, 1.0f / d0.y, 1.0f / d0.z);  // native_recip(ray.dir) (:302)
+    t.tmaxRay = tmaxRay;
+    t.curInst = 0; t.curRank = 0;
+    t.best.wuvt = make_float4(0.0f, 0.0f, 0.0f, tmaxRay);
+    t.best.inst = 0; t.best.tri = 0; t.best.rank = 0;
+    t.cur = sc.rootRef;
+    t.sp = 0;
+}
+
+// One inner-node step: slab-test both children (one aligned 64 B record), descend into the nearer
+// accepted child, push the other.  Requires !(t.cur & REF_LEAF).
+template <bool ANY_HIT, bool COUNT>
+PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+    if (COUNT) st.nodes++;
+    const float4 *np = sc.node64 + 4 * (size_t)t.cur;
+    float4 q0 = PC_LDG(np), q1 = PC_LDG(np + 1), q2 = PC_LDG(np + 2), q3 = PC_LDG(np + 3);
+    float tl = slabEntry(xyz(q0), xyz(q1), t.o, t.invDir, t.tmaxRay);
+    float tr = slabEntry(xyz(q2), xyz(q3), t.o, t.invDir, t.tmaxRay);
+    bool wl = tl < FLT_MAX, wr = tr < FLT_MAX;
+    if (!ANY_HIT) {
+        float lim = t.best.wuvt.w * PC_CULL_SLACK;
+        wl = wl && !(tl > lim);
+        wr = wr && !(tr > lim);
+    }
+    uint32_t lref = f2u(q0.w), rref = f2u(q1.w);
+    if (wl && wr) {
+        bool leftFirst = tl <= tr;
+        stack[t.sp++] = leftFirst ? rref : lref;
+        t.cur = leftFirst ? lref : rref;
+    } else if (wl || wr) {
+        t.cur = wl ? lref : rref;
+    } else {
+        t.cur = t.sp ? stack[--t.sp] : REF_DONE;
+    }
+}
+
+// Reference classes: inner node (bit 31 clear), triangle leaf (bits 31:30 == 10), and the "other"
+// leaf-type references with bits 31:30 == 11 (instance entry, the exit marker, REF_DONE).
+PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
+
+// Instance entry (:237-249) or the exit marker that restores the world-space ray (:330-335).
+// Returns 0 to continue, 1 when the walk is over.  Requires bits 31:30 == 11 and cur != REF_DONE.
+template <bool COUNT>
+PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+    if (t.cur == REF_POP_INSTANCE) {
+        t.o = t.o0; t.d = t.d0;
+        t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
+        if (t.sp == 0) return 1;
+        t.cur = stack[--t.sp];
+        return 0;
+    }
+    if (COUNT) st.instances++;
+    t.curInst = t.cur & 0x3FFFFFFFu;
+    const float4 *ip = sc.inst80 + 5 * (size_t)t.curInst;
+    float4 hdr = PC_LDG(ip);
+    t.curRank = f2u(hdr.z);
+    if (!(f2u(hdr.y) & INST_FLAG_IDENTITY)) {
+        // identity matrices are skipped: x*1 + y*0 + z*0 + 0 == x exactly for finite inputs
+        float4 m0 = PC_LDG(ip + 1), m1 = PC_LDG(ip + 2), m2 = PC_LDG(ip + 3), m3 = PC_LDG(ip + 4);
+        t.o = mul4x1(t.o, m0, m1, m2, m3);
+        t.d = mul3x1(t.d, m0, m1, m2);
+        t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
+        stack[t.sp++] = REF_POP_INSTANCE;
+    }
+    t.cur = f2u(hdr.x);
+    return 0;
+}
+
+// One triangle leaf (:251-291).  Returns 0 to continue, 1 when the walk is over, 2 when an any-hit
+// ray found its occluder.  Requires refIsTriLeaf(t.cur).
+template <bool ANY_HIT, bool COUNT>
+PC_HD int travTris(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+    uint32_t tri = t.cur & 0x3FFFFFFFu;
+    const float4 *tp = sc.tri48 + 3 * (size_t)tri;
+    float4 a = PC_LDG(tp);
+    uint32_t count = f2u(a.w);
+    for (;;) {
+        float4 b = PC_LDG(tp + 1), c = PC_LDG(tp + 2);
+        if (COUNT) st.tris++;
+        float u, v, tt;
+        if (triTest(xyz(a), xyz(b), xyz(c), t.o, t.d, u, v, tt)) {
+            if (ANY_HIT) {
+                if (tt > PC_EPS && tt < t.tmaxRay) return 2;  // (:120-124)
+            } else if (tt > PC_EPS) {                         // (:281)
+                float bt = t.best.wuvt.w;
+                bool closer = tt < bt;
+                // equal t: keep what the reference's visiting order would have kept
+                bool tie = (tt == bt) && bt < t.tmaxRay &&
+                           (t.curRank < t.best.rank || (t.curRank == t.best.rank && tri < t.best.tri));
+                if (closer || tie) {
+                    t.best.wuvt = make_float4(1.0f - (u + v), u, v, tt);
+                    t.best.tri = tri;
+                    t.best.inst = t.curInst;
+                    t.best.rank = t.curRank;
+                }
+            }
+        }
+        if (--count == 0) break;
+        tri++;
+        tp += 3;
+        a = PC_LDG(tp);
+    }
+    if (t.sp == 0) return 1;
+    t.cur = stack[--t.sp];
+    return 0;
+}
+
+// Any leaf-type reference.  Requires t.cur & REF_LEAF.
+template <bool ANY_HIT, bool COUNT>
+PC_HD int travLeaf(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+    if (t.cur == REF_DONE) return 1;
+    if (refIsTriLeaf(t.cur)) return travTris<ANY_HIT, COUNT>(t, sc, stack, st);
+    return travOther<COUNT>(t, sc, stack, st);
+}
+
+// The plain loop: inner-node steps and leaf work in separate loops ("while-while"), so a warp
+// reconverges on "all lanes test boxes" / "all lanes test triangles".  Returns 1 on hit.
 template <bool ANY_HIT, bool COUNT>
 PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &best, TravStats &st) {
     uint32_t stack[PC_STACK_SIZE];
-    int sp = 0;
-    float3 o = o0, d = d0;
-    float3 invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // native_recip(ray.dir) (:302)
-    uint32_t curInst = 0, curRank = 0;
-    best.wuvt = make_float4(0.0f, 0.0f, 0.0f, tmaxRay);
-    best.inst = 0; best.tri = 0; best.rank = 0;
-    uint32_t cur = sc.rootRef;
+    Trav t;
+    travInit(t, sc, o0, d0, tmaxRay);
+    int r;
     for (;;) {
-        // ---- phase 1: walk inner nodes until the current reference is a leaf-type one.  Keeping
-        // the two phases in separate loops lets a warp reconverge on "all lanes test boxes" /
-        // "all lanes test triangles" instead of interleaving both bodies lane by lane.
-        while (!(cur & REF_LEAF)) {
-            if (COUNT) st.nodes++;
-            const float4 *np = sc.node64 + 4 * (size_t)cur;
-            float4 q0 = PC_LDG(np), q1 = PC_LDG(np + 1), q2 = PC_LDG(np + 2), q3 = PC_LDG(np + 3);
-            float tl = slabEntry(xyz(q0), xyz(q1), o, invDir, tmaxRay);
-            float tr = slabEntry(xyz(q2), xyz(q3), o, invDir, tmaxRay);
-            bool wl = tl < FLT_MAX, wr = tr < FLT_MAX;
-            if (!ANY_HIT) {
-                float lim = best.wuvt.w * PC_CULL_SLACK;
-                wl = wl && !(tl > lim);
-                wr = wr && !(tr > lim);
-            }
-            uint32_t lref = f2u(q0.w), rref = f2u(q1.w);
-            if (wl && wr) {
-                bool leftFirst = tl <= tr;
-                stack[sp++] = leftFirst ? rref : lref;
-                cur = leftFirst ? lref : rref;
-            } else if (wl || wr) {
-                cur = wl ? lref : rref;
-            } else {
-                cur = sp ? stack[--sp] : REF_DONE;
-            }
-        }
-        if (cur == REF_DONE) break;
-        // ---- phase 2: leaf-type references
-        if (cur == REF_POP_INSTANCE) {  // left the instance (:330-335)
-            o = o0; d = d0;
-            invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        } else if (cur & REF_TOP) {  // top-level leaf: enter the instance (:237-249)
-            if (COUNT) st.instances++;
-            curInst = cur & 0x3FFFFFFFu;
-            const float4 *ip = sc.inst80 + 5 * (size_t)curInst;
-            float4 hdr = PC_LDG(ip);
-            curRank = f2u(hdr.z);
-            if (!(f2u(hdr.y) & INST_FLAG_IDENTITY)) {
-                // identity matrices are skipped: x*1 + y*0 + z*0 + 0 == x exactly for finite inputs
-                float4 m0 = PC_LDG(ip + 1), m1 = PC_LDG(ip + 2), m2 = PC_LDG(ip + 3), m3 = PC_LDG(ip + 4);
-                o = mul4x1(o, m0, m1, m2, m3);
-                d = mul3x1(d, m0, m1, m2);
-                invDir = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-                stack[sp++] = REF_POP_INSTANCE;
-            }
-            cur = f2u(hdr.x);
-            continue;
-        } else {  // mesh leaf: test its triangles (:251-291)
-            uint32_t tri = cur & 0x3FFFFFFFu;
-            const float4 *tp = sc.tri48 + 3 * (size_t)tri;
-            float4 a = PC_LDG(tp);
-            uint32_t count = f2u(a.w);
-            for (;;) {
-                float4 b = PC_LDG(tp + 1), c = PC_LDG(tp + 2);
-                if (COUNT) st.tris++;
-                float u, v, t;
-                if (triTest(xyz(a), xyz(b), xyz(c), o, d, u, v, t)) {
-                    if (ANY_HIT) {
-                        if (t > PC_EPS && t < tmaxRay) return 1;  // (:120-124)
-                    } else if (t > PC_EPS) {                       // (:281)
-                        float bt = best.wuvt.w;
-                        bool closer = t < bt;
-                        // equal t: keep what the reference's visiting order would have kept
-                        bool tie = (t == bt) && bt < tmaxRay && (curRank < best.rank || (curRank == best.rank && tri < best.tri));
-                        if (closer || tie) {
-                            best.wuvt = make_float4(1.0f - (u + v), u, v, t);
-                            best.tri = tri;
-                            best.inst = curInst;
-                            best.rank = curRank;
-                        }
-                    }
-                }
-                if (--count == 0) break;
-                tri++;
-                tp += 3;
-                a = PC_LDG(tp);
-            }
-        }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        while (!(t.cur & REF_LEAF)) travInner<ANY_HIT, COUNT>(t, sc, stack, st);
+        r = travLeaf<ANY_HIT, COUNT>(t, sc, stack, st);
+        if (r) break;
     }
-    if (ANY_HIT) return 0;
+    best = t.best;
+    if (ANY_HIT) return r == 2 ? 1 : 0;
     return best.wuvt.w < tmaxRay ? 1 : 0;  // (:345)
 }
 

@@ -45,15 +45,27 @@ struct DevBuf {
     }
 };
 
+// What the captured per-sample graph depends on.  Block position / size and the camera are NOT part of
+// it: they reach the kernels through the TraceParams device struct, so the perfect scheduler moving row
+// boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
-    uint32_t frameW = 0, blockY = 0, blockH = 0, nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0;
-    uint64_t sceneEpoch = 0, cameraEpoch = 0;
+    uint32_t nb = 0, rr = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0;
+    uint64_t sceneEpoch = 0;
+    const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
-        return frameW == o.frameW && blockY == o.blockY && blockH == o.blockH && nb == o.nb && rr == o.rr &&
-               counters == o.counters && packets == o.packets && reforder == o.reforder && fixq4 == o.fixq4 &&
-               sceneEpoch == o.sceneEpoch && cameraEpoch == o.cameraEpoch;
+        return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
+               fixq4 == o.fixq4 && chains == o.chains && sceneEpoch == o.sceneEpoch && seedsPtr == o.seedsPtr;
     }
+};
+
+constexpr int MAX_CHAINS = 8;
+constexpr int GRAPH_SAMPLES_PER_CHAIN = 4;  // samples each chain contributes to one replay of the captured graph
+struct Chain {
+    DevBuf rays[3], paths, hitFlags, hits, emSamples, ctl, status, acc;  // acc: chains > 0 only
+    FrameBufs fb{};
+    cudaStream_t stream = nullptr;  // chain 0 uses the handle's stream
+    cudaEvent_t evJoin = nullptr;
 };
 
 }  // namespace
@@ -74,13 +86,21 @@ struct pc_tracer {
     uint64_t sceneEpoch = 0, cameraEpoch = 0;
     // frame
     uint32_t W = 0, H = 0;
-    DevBuf rays[3], paths, hitFlags, hits, emSamples, traceAcc, frameAcc, frameBuf, ctl, status, seedsDev, scratch;
-    FrameBufs fb{};
+    DevBuf traceAcc, frameAcc, frameBuf, seedsDev, scratch, params;
+    // Sample chains.  The samples of a block request are independent given their seeds, and one sample's
+    // launches (a few hundred thousand rays each at the BASELINE sizes) leave the machine idle in their
+    // tails, so chain c traces samples c, c+nChains, ... with its own ray / path / hit state on its own
+    // stream, and the chains' launches overlap.  Chain 0 accumulates into the trace accumulator, every
+    // other chain into its own, added to it once at the end of pc_trace in chain order (deterministic).
+    Chain chain[MAX_CHAINS];
+    int nChains = 0;        // chains with allocated state
+    int lastChain = 0;      // chain that traced the last sample of the last pc_trace (pc_read_buffer)
     size_t statusStride = 0;  // words per bounce
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 1, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0;
+    int optCounters = 0, optPackets = 1, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4;
+    cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
     std::vector<int> timerClass;
     // graph cache
@@ -168,21 +188,21 @@ struct LaunchTimer {
 };
 
 template <bool COUNT>
-void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launches) {
-    cudaStream_t s = tr->stream;
-    TraceCtl *ctl = (TraceCtl *)tr->ctl.p;
+void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches) {
+    cudaStream_t s = ch.stream;
+    TraceCtl *ctl = (TraceCtl *)ch.ctl.p;
     const uint32_t *seeds = (const uint32_t *)tr->seedsDev.p;
-    unsigned long long *status = (unsigned long long *)tr->status.p;
+    unsigned long long *status = (unsigned long long *)ch.status.p;
     const uint32_t nb = req.num_bounces, perSample = 1 + nb;
-    const uint32_t N = req.frame_w * req.block_h;
     const int pg = tr->persistentGrid;
     const int shadeGrid = tr->shadeGrid;
-    (void)N;
+    const TraceParams *params = (const TraceParams *)tr->params.p;
+    const FrameBufs &fb = ch.fb;
     uint64_t L = 0;
     size_t statusWords = tr->statusStride * nb;
     {
         LaunchTimer lt(tr, PC_K_BEGIN_SAMPLE);
-        k_begin_sample<<<grid_for(statusWords, 256, 1024), 256, 0, s>>>(ctl, status, statusWords);
+        k_begin_sample<<<grid_for(statusWords, 256, 1024), 256, 0, s>>>(ctl, status, statusWords, sampleStride);
     }
     L++;
     int slot = 0;
@@ -190,11 +210,11 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
     {
     LaunchTimer lt(tr, PC_K_PRIMARY);
     if (tr->optRefOrder)
-        k_primary<2, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+        k_primary<2, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
     else if (tr->optPackets)
-        k_primary<1, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+        k_primary<1, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
     else
-        k_primary<0, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, tr->cam, req.frame_w, req.block_y, req.block_h, perSample, slot);
+        k_primary<0, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
     }
     L++;
     slot++;
@@ -203,7 +223,7 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
         // ShadePrimaryRayMisses / ShadeIndirectRayMisses + ShadeHits (pipeline.go:134-146)
         {
             LaunchTimer lt(tr, PC_K_SHADE);
-            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, 0, s>>>(tr->sc, tr->fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
+            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
                                                             perSample, bounce, req.min_bounces_for_rr, a, tr->optFixQ4);
         }
         L++;
@@ -211,9 +231,9 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
         if (tr->optRefOrder)
-            k_occlusion<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[2], tr->fb.paths, tr->fb.emissiveSamples, tr->fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
         else
-            k_occlusion<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[2], tr->fb.paths, tr->fb.emissiveSamples, tr->fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
         }
         L++;
         slot++;
@@ -221,9 +241,9 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
             a = 1 - a;
             LaunchTimer lt(tr, PC_K_QUERY);
             if (tr->optRefOrder)
-                k_query<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[a], tr->fb.hitFlags, tr->fb.hits, ctl, a, slot);
+                k_query<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot);
             else
-                k_query<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[a], tr->fb.hitFlags, tr->fb.hits, ctl, a, slot);
+                k_query<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot);
             L++;
             slot++;
         }
@@ -231,9 +251,75 @@ void record_sample_t(pc_tracer *tr, const pc_block_request &req, uint64_t *launc
     *launches = L;
 }
 
-void record_sample(pc_tracer *tr, const pc_block_request &req, uint64_t *launches) {
-    if (tr->optCounters) record_sample_t<true>(tr, req, launches);
-    else record_sample_t<false>(tr, req, launches);
+void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches) {
+    if (tr->optCounters) record_sample_t<true>(tr, ch, req, sampleStride, launches);
+    else record_sample_t<false>(tr, ch, req, sampleStride, launches);
+}
+
+// Enqueue perChain[c] samples on every chain c < nChains: fork the chain streams off the handle's stream,
+// let each chain run its samples back to back, join.  Works identically under stream capture (the fork /
+// join events become graph dependencies and the chains become parallel branches of the graph).
+int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, const uint32_t *perChain, uint64_t *launchesPerSample) {
+    cudaStream_t s0 = tr->stream;
+    if (nChains > 1) {
+        if (cudaEventRecord(tr->evFork, s0) != cudaSuccess) return 1;
+        for (int c = 1; c < nChains; c++)
+            if (perChain[c] && cudaStreamWaitEvent(tr->chain[c].stream, tr->evFork, 0) != cudaSuccess) return 1;
+    }
+    for (int c = 0; c < nChains; c++)
+        for (uint32_t k = 0; k < perChain[c]; k++) record_sample(tr, tr->chain[c], req, (uint32_t)nChains, launchesPerSample);
+    for (int c = 1; c < nChains; c++) {
+        if (!perChain[c]) continue;
+        if (cudaEventRecord(tr->chain[c].evJoin, tr->chain[c].stream) != cudaSuccess) return 1;
+        if (cudaStreamWaitEvent(s0, tr->chain[c].evJoin, 0) != cudaSuccess) return 1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
+// (Re)allocate the per-chain state for the current frame size.
+int ensure_chains(pc_tracer *tr, int want) {
+    if (want < 1) want = 1;
+    if (want > MAX_CHAINS) want = MAX_CHAINS;
+    const size_t px = (size_t)tr->W * tr->H;
+    for (int c = tr->nChains; c < want; c++) {
+        Chain &ch = tr->chain[c];
+        if (c == 0) ch.stream = tr->stream;
+        else if (!ch.stream) {
+            CU(tr, PC_ERR_ALLOC, cudaStreamCreateWithFlags(&ch.stream, cudaStreamNonBlocking));
+            CU(tr, PC_ERR_ALLOC, cudaEventCreateWithFlags(&ch.evJoin, cudaEventDisableTiming));
+        }
+        for (auto &r : ch.rays) CU(tr, PC_ERR_ALLOC, r.alloc(px * 32));
+        CU(tr, PC_ERR_ALLOC, ch.paths.alloc(px * 32));
+        CU(tr, PC_ERR_ALLOC, ch.hitFlags.alloc(px * 4));
+        CU(tr, PC_ERR_ALLOC, ch.hits.alloc(px * 32));
+        CU(tr, PC_ERR_ALLOC, ch.emSamples.alloc(px * 16));
+        CU(tr, PC_ERR_ALLOC, ch.status.alloc(tr->statusStride * MAX_BOUNCES * 8));
+        if (!ch.ctl.p) {
+            CU(tr, PC_ERR_ALLOC, ch.ctl.alloc(sizeof(TraceCtl)));
+            CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.ctl.p, 0, sizeof(TraceCtl), tr->stream));
+        }
+        if (c > 0) CU(tr, PC_ERR_ALLOC, ch.acc.alloc(px * 16));
+        for (int i = 0; i < 3; i++) ch.fb.rays[i] = (Ray *)ch.rays[i].p;
+        ch.fb.paths = (PathRec *)ch.paths.p;
+        ch.fb.hitFlags = (uint32_t *)ch.hitFlags.p;
+        ch.fb.hits = (HitRec *)ch.hits.p;
+        ch.fb.emissiveSamples = (float4 *)ch.emSamples.p;
+        ch.fb.traceAcc = (float4 *)(c == 0 ? tr->traceAcc.p : ch.acc.p);
+        DevBuf *zero[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status};
+        for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
+        if (c > 0) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.acc.p, 0, ch.acc.bytes, tr->stream));
+        tr->nChains = c + 1;
+    }
+    return 0;
+}
+
+void release_chain_buffers(pc_tracer *tr) {
+    for (int c = 0; c < MAX_CHAINS; c++) {
+        Chain &ch = tr->chain[c];
+        DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.acc};
+        for (DevBuf *b : all) b->release();
+    }
+    tr->nChains = 0;
 }
 
 int upload(pc_tracer *tr, DevBuf &b, const void *src, size_t bytes) {
@@ -307,8 +393,11 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&tr->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&tr->evStart);
     if (e == cudaSuccess) e = cudaEventCreate(&tr->evStop);
-    if (e == cudaSuccess) e = tr->ctl.alloc(sizeof(TraceCtl));
-    if (e == cudaSuccess) e = cudaMemsetAsync(tr->ctl.p, 0, sizeof(TraceCtl), tr->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&tr->evFork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = tr->chain[0].ctl.alloc(sizeof(TraceCtl));
+    if (e == cudaSuccess) e = tr->params.alloc(sizeof(TraceParams));
+    if (e == cudaSuccess) e = cudaMemsetAsync(tr->chain[0].ctl.p, 0, sizeof(TraceCtl), tr->stream);
+    tr->chain[0].stream = tr->stream;
     if (e != cudaSuccess) {
         fail(nullptr, PC_ERR_NO_DEVICE, "pc_create(%d): %s", ordinal, cudaGetErrorString(e));
         delete tr;
@@ -337,9 +426,15 @@ void pc_destroy(pc_tracer *tr) {
         if (tr->stream) cudaStreamSynchronize(tr->stream);
         drop_graph(tr);
         DevBuf *all[] = {&tr->bvh, &tr->inst, &tr->mats, &tr->texData, &tr->texMeta, &tr->verts, &tr->normals, &tr->uvs,
-                         &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->rays[0], &tr->rays[1],
-                         &tr->rays[2], &tr->paths, &tr->hitFlags, &tr->hits, &tr->emSamples, &tr->traceAcc, &tr->frameAcc,
-                         &tr->frameBuf, &tr->ctl, &tr->status, &tr->seedsDev, &tr->scratch};
+                         &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->traceAcc, &tr->frameAcc,
+                         &tr->frameBuf, &tr->seedsDev, &tr->scratch, &tr->params};
+        release_chain_buffers(tr);
+        for (int c = 0; c < MAX_CHAINS; c++) {
+            tr->chain[c].ctl.release();
+            if (c > 0 && tr->chain[c].stream) cudaStreamDestroy(tr->chain[c].stream);
+            if (tr->chain[c].evJoin) cudaEventDestroy(tr->chain[c].evJoin);
+        }
+        if (tr->evFork) cudaEventDestroy(tr->evFork);
         for (DevBuf *b : all) b->release();
         for (cudaEvent_t e : tr->timerEvents) cudaEventDestroy(e);
         if (tr->evStart) cudaEventDestroy(tr->evStart);
@@ -372,6 +467,10 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_USE_GRAPH: tr->optGraph = value != 0; break;
         case PC_OPT_FIX_Q4: tr->optFixQ4 = value != 0; break;
         case PC_OPT_KERNEL_TIMERS: tr->optTimers = value != 0; break;
+        case PC_OPT_SAMPLE_CHAINS:
+            if (value < 1 || value > MAX_CHAINS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample chains must be in [1, %d]", MAX_CHAINS);
+            tr->optChains = value;
+            break;
         default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown option %d", option);
     }
     return 0;
@@ -390,28 +489,17 @@ int pc_resize(pc_tracer *tr, uint32_t w, uint32_t h) {
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
     drop_graph(tr);
     const size_t px = (size_t)w * h;
-    for (auto &r : tr->rays) CU(tr, PC_ERR_ALLOC, r.alloc(px * 32));
-    CU(tr, PC_ERR_ALLOC, tr->paths.alloc(px * 32));
-    CU(tr, PC_ERR_ALLOC, tr->hitFlags.alloc(px * 4));
-    CU(tr, PC_ERR_ALLOC, tr->hits.alloc(px * 32));
-    CU(tr, PC_ERR_ALLOC, tr->emSamples.alloc(px * 16));
+    release_chain_buffers(tr);
     CU(tr, PC_ERR_ALLOC, tr->traceAcc.alloc(px * 16));
     CU(tr, PC_ERR_ALLOC, tr->frameAcc.alloc(px * 16));
     CU(tr, PC_ERR_ALLOC, tr->frameBuf.alloc(px * 4));
     CU(tr, PC_ERR_ALLOC, tr->scratch.alloc(px * 32));
     tr->statusStride = (px + 31) / 32 + 1;  // one status word per 32-ray tile
-    CU(tr, PC_ERR_ALLOC, tr->status.alloc(tr->statusStride * MAX_BOUNCES * 8));
     tr->W = w;
     tr->H = h;
-    for (int i = 0; i < 3; i++) tr->fb.rays[i] = (Ray *)tr->rays[i].p;
-    tr->fb.paths = (PathRec *)tr->paths.p;
-    tr->fb.hitFlags = (uint32_t *)tr->hitFlags.p;
-    tr->fb.hits = (HitRec *)tr->hits.p;
-    tr->fb.emissiveSamples = (float4 *)tr->emSamples.p;
-    tr->fb.traceAcc = (float4 *)tr->traceAcc.p;
-    DevBuf *zero[] = {&tr->rays[0], &tr->rays[1], &tr->rays[2], &tr->paths, &tr->hitFlags, &tr->hits, &tr->emSamples,
-                      &tr->traceAcc, &tr->frameAcc, &tr->frameBuf, &tr->status};
+    DevBuf *zero[] = {&tr->traceAcc, &tr->frameAcc, &tr->frameBuf};
     for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
+    if ((rc = ensure_chains(tr, 1))) return rc;  // further chains are allocated by the first pc_trace that wants them
     tr->frameOpen = tr->frameOpenByMerge = false;
     return 0;
 }
@@ -522,26 +610,48 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     if ((rc = clear_acc(tr, tr->traceAcc))) return rc;  // ClearTraceAccumulator (tracer.go:215)
     if (need * 4 > tr->seedsDev.bytes) CU(tr, PC_ERR_ALLOC, tr->seedsDev.alloc(need * 4 + 4096));
     if (need) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->seedsDev.p, seeds, need * 4, cudaMemcpyHostToDevice, s));
-    // reset the persistent part of the control block, keep the three ray counters
-    CU(tr, PC_ERR_KERNEL, cudaMemsetAsync((char *)tr->ctl.p + offsetof(TraceCtl, nextSample), 0,
-                                          sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
+    TraceParams hp;
+    hp.cam = tr->cam;
+    hp.frameW = req->frame_w; hp.blockY = req->block_y; hp.blockH = req->block_h; hp.pad = 0;
+    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->params.p, &hp, sizeof(hp), cudaMemcpyHostToDevice, s));
+    // ---- sample chains: chain c traces samples c, c + nc, c + 2 nc, ...
+    int nc = tr->optTimers ? 1 : tr->optChains;
+    if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
+    if ((rc = ensure_chains(tr, nc))) return rc;
+    static const uint32_t kChainIndex[MAX_CHAINS] = {0, 1, 2, 3, 4, 5, 6, 7};
+    for (int c = 0; c < nc; c++) {
+        // reset the persistent part of the control block, keep the three ray counters
+        char *ctl = (char *)tr->chain[c].ctl.p;
+        CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + offsetof(TraceCtl, nextSample), 0, sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
+        if (c > 0) {
+            CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl + offsetof(TraceCtl, nextSample), &kChainIndex[c], 4, cudaMemcpyHostToDevice, s));
+            if ((rc = clear_acc(tr, tr->chain[c].acc))) return rc;
+        }
+    }
     uint64_t launches = 2;
     uint64_t perSampleLaunches = 0;
     CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStart, s));
     if (spp > 0) {
         tr->timerClass.clear();
-        if (tr->optGraph && !tr->optTimers) {
+        uint32_t done = 0;
+        if (tr->optGraph && !tr->optTimers && spp >= (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc)) {
             GraphKey key;
-            key.frameW = req->frame_w; key.blockY = req->block_y; key.blockH = req->block_h;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.sceneEpoch = tr->sceneEpoch; key.cameraEpoch = tr->cameraEpoch;
+            key.chains = nc; key.sceneEpoch = tr->sceneEpoch; key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;
+                uint32_t perChain[MAX_CHAINS] = {};
+                for (int c = 0; c < nc; c++) perChain[c] = GRAPH_SAMPLES_PER_CHAIN;
                 CU(tr, PC_ERR_KERNEL, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                record_sample(tr, *req, &tr->launchesPerSample);
-                CU(tr, PC_ERR_KERNEL, cudaStreamEndCapture(s, &graph));
+                int bad = enqueue_chains(tr, *req, nc, perChain, &tr->launchesPerSample);
+                cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                if (bad || ce != cudaSuccess) {
+                    if (graph) cudaGraphDestroy(graph);
+                    tr->dead = true;
+                    return fail(tr, PC_ERR_KERNEL, "stream capture of the sample graph failed: %s", cudaGetErrorString(ce != cudaSuccess ? ce : cudaGetLastError()));
+                }
                 cudaError_t e = cudaGraphInstantiate(&tr->graphExec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) {
@@ -551,13 +661,24 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
                 tr->graphKey = key;
             }
             perSampleLaunches = tr->launchesPerSample;
-            for (uint32_t i = 0; i < spp; i++) CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
-        } else {
-            for (uint32_t i = 0; i < spp; i++) {
-                record_sample(tr, *req, &perSampleLaunches);
-                CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+            const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc);
+            for (; done + perGraph <= spp; done += perGraph) CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
+        }
+        if (done < spp) {  // the remainder (or everything, without graphs): same chain assignment, direct launches
+            uint32_t perChain[MAX_CHAINS] = {};
+            for (uint32_t i = done; i < spp; i++) perChain[i % (uint32_t)nc]++;
+            if (enqueue_chains(tr, *req, nc, perChain, &perSampleLaunches)) {
+                tr->dead = true;
+                return fail(tr, PC_ERR_KERNEL, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
         }
+        // chains > 0 accumulated into their own buffers: add them in chain order
+        const size_t px = (size_t)tr->W * tr->H;
+        for (int c = 1; c < nc; c++) {
+            k_merge<<<grid_for(px, 256, tr->prop.multiProcessorCount * 8), 256, 0, s>>>((float4 *)tr->traceAcc.p, (const float4 *)tr->chain[c].acc.p, 0, 0, px);
+            launches++;
+        }
+        tr->lastChain = (int)((spp - 1) % (uint32_t)nc);
     }
     CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStop, s));
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(s));
@@ -565,7 +686,12 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     float ms = 0.f;
     cudaEventElapsedTime(&ms, tr->evStart, tr->evStop);
     TraceCtl hc;
-    CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(&hc, tr->ctl.p, sizeof(hc), cudaMemcpyDeviceToHost));
+    memset(&hc, 0, sizeof(hc));
+    for (int c = 0; c < nc; c++) {
+        TraceCtl one;
+        CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(&one, tr->chain[c].ctl.p, sizeof(one), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < ST_COUNT; k++) hc.stats[k] += one.stats[k];
+    }
     if (spp) req->seed = seeds[(size_t)perSample * (spp - 1)];  // the last camera seed (tracer.go:222)
     req->accumulated_samples += spp;                             // tracer.go:240
     pc_stats &st = tr->stats;
@@ -690,16 +816,18 @@ int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes) {
     std::lock_guard<std::mutex> g(tr->mu);
     const void *src = nullptr;
     size_t have = 0;
+    const Chain &lc = tr->chain[tr->lastChain < tr->nChains ? tr->lastChain : 0];
     switch (which) {
-        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: src = tr->rays[which].p; have = tr->rays[which].bytes; break;
-        case PC_BUF_PATHS: src = tr->paths.p; have = tr->paths.bytes; break;
-        case PC_BUF_HIT_FLAGS: src = tr->hitFlags.p; have = tr->hitFlags.bytes; break;
-        case PC_BUF_INTERSECTIONS: src = tr->hits.p; have = tr->hits.bytes; break;
-        case PC_BUF_EMISSIVE_SAMPLES: src = tr->emSamples.p; have = tr->emSamples.bytes; break;
+        // per-sample state: the buffers of the chain that traced the LAST sample (what the reference's single set would hold)
+        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: src = lc.rays[which].p; have = lc.rays[which].bytes; break;
+        case PC_BUF_PATHS: src = lc.paths.p; have = lc.paths.bytes; break;
+        case PC_BUF_HIT_FLAGS: src = lc.hitFlags.p; have = lc.hitFlags.bytes; break;
+        case PC_BUF_INTERSECTIONS: src = lc.hits.p; have = lc.hits.bytes; break;
+        case PC_BUF_EMISSIVE_SAMPLES: src = lc.emSamples.p; have = lc.emSamples.bytes; break;
         case PC_BUF_TRACE_ACCUMULATOR: src = tr->traceAcc.p; have = tr->traceAcc.bytes; break;
         case PC_BUF_FRAME_ACCUMULATOR: src = tr->frameAcc.p; have = tr->frameAcc.bytes; break;
         case PC_BUF_FRAME_BUFFER: src = tr->frameBuf.p; have = tr->frameBuf.bytes; break;
-        case PC_BUF_RAY_COUNTERS: src = tr->ctl.p; have = 12; break;
+        case PC_BUF_RAY_COUNTERS: src = lc.ctl.p; have = 12; break;
         default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown buffer %d", which);
     }
     if (!src || bytes > have) return fail(tr, PC_ERR_INVALID_ARGUMENT, "buffer %d holds %zu bytes, %llu requested", which, have, (unsigned long long)bytes);
@@ -715,26 +843,27 @@ int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode, ui
     if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
     if ((size_t)n > (size_t)tr->W * tr->H) return fail(tr, PC_ERR_INVALID_ARGUMENT, "%u rays exceed the frame's ray buffer", n);
     cudaStream_t s = tr->stream;
-    TraceCtl *ctl = (TraceCtl *)tr->ctl.p;
-    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->rays[0].p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    Chain &c0 = tr->chain[0];
+    TraceCtl *ctl = (TraceCtl *)c0.ctl.p;
+    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(c0.rays[0].p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, s));
     CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl, 0, sizeof(TraceCtl), s));
     int cnt[3] = {(int)n, 0, (int)n};
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl, cnt, 12, cudaMemcpyHostToDevice, s));
     const int pg = tr->persistentGrid;
     if (mode == 0) {
-        if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, 0, 0);
-        else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, 0, 0);
+        if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0);
+        else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0);
     } else if (mode == 1) {
-        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.paths, tr->fb.emissiveSamples, nullptr, tr->fb.hitFlags, ctl, 0);
-        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.paths, tr->fb.emissiveSamples, nullptr, tr->fb.hitFlags, ctl, 0);
+        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0);
+        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0);
     } else if (mode == 2) {
-        k_debug_packet<false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, tr->fb.rays[0], tr->fb.hitFlags, tr->fb.hits, ctl, n, 0);
+        k_debug_packet<false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, n, 0);
     } else {
         return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown intersect mode %d", mode);
     }
     CU(tr, PC_ERR_KERNEL, cudaGetLastError());
-    if (out_flags) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_flags, tr->hitFlags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
-    if (out_hits && mode != 1) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_hits, tr->hits.p, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
+    if (out_flags) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_flags, c0.hitFlags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (out_hits && mode != 1) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(out_hits, c0.hits.p, (size_t)n * 32, cudaMemcpyDeviceToHost, s));
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(s));
     return 0;
 }

@@ -32,6 +32,9 @@ constexpr int SHADE_BLOCK = 128;  // 4 warps
 #ifndef SHADE_MIN_BLOCKS
 #define SHADE_MIN_BLOCKS 6
 #endif
+#ifndef PC_TRAV_MIN_BLOCKS
+#define PC_TRAV_MIN_BLOCKS 8
+#endif
 
 enum StatIdx {
     ST_QUERY_RAYS = 0, ST_OCCLUSION_RAYS, ST_NODES, ST_TRIS, ST_INSTANCES, ST_SHADED, ST_OCC_EMITTED,
@@ -48,6 +51,15 @@ struct TraceCtl {
     unsigned long long stats[ST_COUNT];  // [persist]
     uint32_t queueHead[2 * MAX_BOUNCES + 2];  // [sample] work-queue heads, one per traversal launch
     uint32_t ticket[MAX_BOUNCES];             // [sample] block tickets of the shade launches
+    uint32_t expCnt[MAX_BOUNCES][3];          // [sample] PC_EXPERIMENT_UNORDERED only
+};
+
+// Per-pc_trace parameters that change from block to block or frame to frame (camera moves, the
+// schedulers re-assigning rows).  They live in device memory and are refreshed by a stream-ordered
+// copy, so the captured per-sample graph never has to be re-instantiated for them.
+struct TraceParams {
+    CameraParams cam;
+    uint32_t frameW, blockY, blockH, pad;
 };
 
 struct Ray { float4 origin, dir; };                     // types.cl:4-10
@@ -65,6 +77,19 @@ struct FrameBufs {
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// Ray / path / hit state is written once and read once per bounce (a stream of 100+ MB per launch at
+// the BASELINE sizes) while the scene's nodes and triangles are re-read by every ray: the state goes
+// through the cache-streaming path (ld.global.cs / st.global.cs, evict-first) so it does not push the
+// scene out of L1/L2.
+__device__ __forceinline__ Ray ld_ray(const Ray *p) { Ray r; r.origin = __ldcs(&p->origin); r.dir = __ldcs(&p->dir); return r; }
+__device__ __forceinline__ void st_ray(Ray *p, float4 origin, float4 dir) { __stcs(&p->origin, origin); __stcs(&p->dir, dir); }
+__device__ __forceinline__ HitRec ld_hit(const HitRec *p) { HitRec h; h.wuvt = __ldcs(&p->wuvt); h.meta = __ldcs(&p->meta); return h; }
+__device__ __forceinline__ void st_hit(HitRec *p, float4 wuvt, uint32_t inst, uint32_t tri) {
+    __stcs(&p->wuvt, wuvt);
+    __stcs(&p->meta, make_uint4(inst, tri, 0u, 0u));
+}
+__device__ __forceinline__ PathRec ld_path(const PathRec *p) { PathRec r; r.throughput = __ldcs(&p->throughput); r.meta = __ldcs(&p->meta); return r; }
+
 __device__ __forceinline__ void warp_add_stat(TraceCtl *ctl, int idx, uint32_t v) {
     v = __reduce_add_sync(0xFFFFFFFFu, v);
     if (lane_id() == 0 && v) atomicAdd(&ctl->stats[idx], (unsigned long long)v);
@@ -78,17 +103,170 @@ __device__ __forceinline__ uint32_t next_unit(uint32_t *head) {
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords) {
+__global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords, uint32_t sampleStride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    if (i == 0) {
+    if (i == 0) {  // a chain traces every sampleStride-th sample of the block request
         ctl->curSample = ctl->nextSample;
-        ctl->nextSample = ctl->nextSample + 1;
+        ctl->nextSample = ctl->nextSample + sampleStride;
     }
     if (i < 2 * MAX_BOUNCES + 2) ctl->queueHead[i] = 0;
-    if (i < MAX_BOUNCES) ctl->ticket[i] = 0;
+    if (i < MAX_BOUNCES) { ctl->ticket[i] = 0; ctl->expCnt[i][0] = 0; ctl->expCnt[i][1] = 0; ctl->expCnt[i][2] = 0; }
     for (size_t k = i; k < statusWords; k += stride) status[k] = 0ull;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Persistent per-ray traversal with warp-level refilling.
+//
+// A warp keeps up to 32 rays in flight and every lane runs the Trav state machine of pc_device.cuh.
+// Measured on the Cornell configs (ncu, profiles/) a plain "32 rays per warp, while-while" loop keeps
+// only 8.7 of 32 lanes busy: lanes that found their triangle leaf wait for the slowest lane's search,
+// lanes with a 2-triangle leaf wait for a 10-triangle one, finished lanes wait for the longest ray.
+// The schedule below (modelled lane by lane on real bounce rays with tools/simt_model.py before it was
+// written: 0.29 -> 0.62 SIMD efficiency) attacks all three:
+//   * refill    -- when fewer than PC_REFILL_THRESHOLD lanes hold a ray the idle lanes take new rays
+//                  from the global queue.  The queue's atomicAdd is issued one batch AHEAD and only
+//                  consumed (shuffled out of lane 0) when the previous batch is used up, so its
+//                  latency overlaps traversal instead of stalling the warp;
+//   * phase 1   -- search: inner-node steps, instance entries and exit markers, until the lane holds
+//                  a triangle leaf.  Bounded: once fewer than PC_SEARCH_MIN lanes are still searching
+//                  while others already hold a leaf, the warp moves on and the stragglers resume
+//                  their search in the next round;
+//   * phase 2   -- every lane that holds a triangle leaf tests its triangles; finished rays are
+//                  committed and their lanes become idle.
+// Which lane traces which ray changes nothing: a ray's result depends on that ray alone and is written
+// to the slot of its index.
+//   Source::load(i, o, d, tmax)   fetch (or generate) ray i
+//   Sink::store(i, hit, trav)     consume the finished traversal of ray i
+// ------------------------------------------------------------------------------------------------
+// MEASURED (B200, config 2, profiles/ab_r01_traversal.txt): the refilling schedule executes 23 % fewer warp
+// instructions and raises lane efficiency from 8.7 to 13.6 of 32, but its extra per-lane state costs 79
+// registers instead of 64 (6 instead of 8 resident blocks per SM) and the kernel is latency bound, so IPC
+// falls with occupancy (2.18 -> 1.51) and k_query gets SLOWER (129 -> 148 us).  It therefore stays off by
+// default (PC_TRACE_REFILL=0: fixed 32-ray units through traverse()) until the state fits 64 registers.
+#ifndef PC_TRACE_REFILL
+#define PC_TRACE_REFILL 0
+#endif
+#ifndef PC_REFILL_THRESHOLD
+#define PC_REFILL_THRESHOLD 26
+#endif
+#ifndef PC_SEARCH_MIN
+#define PC_SEARCH_MIN 8
+#endif
+#define PC_QUEUE_BATCH 32u
+
+#if !PC_TRACE_REFILL
+// Fixed units: a warp pulls 32 consecutive rays and every lane walks its ray with traverse().
+template <bool ANY_HIT, bool COUNT, class Source, class Sink>
+__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink) {
+    for (;;) {
+        const uint32_t unit = next_unit(head);
+        if (unit >= n) break;
+        const uint32_t i = unit + lane_id();
+        if (i < n) {
+            float3 o, d;
+            float tmax;
+            src.load(i, o, d, tmax);
+            Trav t;
+            const int hit = traverse<ANY_HIT, COUNT>(sc, o, d, tmax, t.best, st);
+            t.tmaxRay = tmax;
+            sink.store(i, hit, t);
+        }
+    }
+}
+#else
+template <bool ANY_HIT, bool COUNT, class Source, class Sink>
+__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const unsigned lane = lane_id();
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint32_t stack[PC_STACK_SIZE];
+    Trav t;
+    t.cur = REF_DONE; t.sp = 0;
+    uint32_t rayIndex = 0;
+    bool busy = false;          // this lane holds a live ray
+    bool exhausted = false;     // warp-uniform: the queue has nothing left for this warp
+    uint32_t poolNext = 0, poolEnd = 0;  // warp-uniform: ray indices already claimed from the queue
+    uint32_t ahead = 0;         // lane 0: base of the batch claimed one step ahead
+    if (lane == 0) ahead = atomicAdd(head, PC_QUEUE_BATCH);
+    for (;;) {
+        // ---- refill idle lanes
+        const unsigned idle = __ballot_sync(FULL, !busy);
+        if (idle && !exhausted) {
+            const uint32_t want = __popc(idle), myRank = __popc(idle & ltMask);
+            uint32_t assigned = 0;
+            while (assigned < want) {
+                if (poolNext == poolEnd) {
+                    const uint32_t base = __shfl_sync(FULL, ahead, 0);
+                    if (base >= n) { exhausted = true; break; }
+                    poolNext = base;
+                    poolEnd = min(base + PC_QUEUE_BATCH, n);
+                    if (lane == 0) ahead = atomicAdd(head, PC_QUEUE_BATCH);
+                }
+                const uint32_t take = min(want - assigned, poolEnd - poolNext);
+                if (!busy && myRank >= assigned && myRank < assigned + take) {
+                    const uint32_t i = poolNext + (myRank - assigned);
+                    float3 o, d;
+                    float tmax;
+                    src.load(i, o, d, tmax);
+                    travInit(t, sc, o, d, tmax);
+                    rayIndex = i;
+                    busy = true;
+                }
+                poolNext += take;
+                assigned += take;
+            }
+        }
+        if (!__any_sync(FULL, busy)) break;
+        // ---- rounds of (search, triangles) until too few lanes are busy
+        for (;;) {
+            for (;;) {  // phase 1
+                const bool searching = busy && !refIsTriLeaf(t.cur) && t.cur != REF_DONE;
+                const unsigned sm = __ballot_sync(FULL, searching);
+                if (sm == 0u) break;
+                if (__popc(sm) < PC_SEARCH_MIN && __any_sync(FULL, busy && refIsTriLeaf(t.cur))) break;
+                if (searching) {
+                    if (!(t.cur & REF_LEAF)) {
+                        travInner<ANY_HIT, COUNT>(t, sc, stack, st);
+                    } else if (travOther<COUNT>(t, sc, stack, st)) {
+                        t.cur = REF_DONE;
+                    }
+                }
+            }
+            if (busy && (refIsTriLeaf(t.cur) || t.cur == REF_DONE)) {  // phase 2
+                const int r = t.cur == REF_DONE ? 1 : travTris<ANY_HIT, COUNT>(t, sc, stack, st);
+                if (r) {
+                    const int hit = ANY_HIT ? (r == 2 ? 1 : 0) : (t.best.wuvt.w < t.tmaxRay ? 1 : 0);
+                    sink.store(rayIndex, hit, t);
+                    busy = false;
+                }
+            }
+            const unsigned live = __ballot_sync(FULL, busy);
+            if (live == 0u) break;
+            if (!exhausted && __popc(live) < PC_REFILL_THRESHOLD) break;
+        }
+    }
+}
+#endif
+
+struct RaySource {  // rays[i] as stored by k_primary / k_shade
+    const Ray *rays;
+    __device__ __forceinline__ void load(uint32_t i, float3 &o, float3 &d, float &tmax) const {
+        const Ray r = ld_ray(rays + i);
+        o = xyz(r.origin); d = xyz(r.dir); tmax = r.origin.w;
+    }
+};
+template <bool COUNT>
+struct HitSink {  // hitFlag + Intersection record (intersect.cl:345-346)
+    uint32_t *hitFlags;
+    HitRec *hits;
+    uint32_t missed;
+    __device__ __forceinline__ void store(uint32_t i, int hit, const Trav &t) {
+        __stcs(hitFlags + i, (uint32_t)hit);
+        st_hit(hits + i, t.best.wuvt, t.best.inst, t.best.tri);
+        if (COUNT && !hit) missed++;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Warp-packet closest-hit traversal: one node sequence per warp, stack of (reference, lane mask)
@@ -198,64 +376,83 @@ __device__ __forceinline__ int traverse_packet(const DScene &sc, uint2 *stack, b
     return best.wuvt.w < tmaxRay ? 1 : 0;
 }
 
+// generatePrimaryRays (camera.cl:5-58) as a ray source: ray i is pixel (i % frameW, i / frameW) of the block
+struct PrimarySource {
+    FrameBufs fb;
+    CameraParams cam;
+    uint32_t frameW, blockY, randSeed;
+    __device__ __forceinline__ void load(uint32_t index, float3 &o, float3 &d, float &tmax) const {
+        const uint32_t gx = index % frameW, gy = index / frameW;
+        d = primaryRayDir(cam, gx, gy, blockY, randSeed);
+        o = cam.eye;
+        tmax = FLT_MAX;
+        st_ray(fb.rays[0] + index, f4(cam.eye, FLT_MAX), f4(d, (float)index));  // rayNew (util/ray.cl:13-16)
+        // pathNew (util/path.cl:13-17)
+        __stcs(&fb.paths[index].throughput, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+        __stcs(&fb.paths[index].meta, make_uint4((gy + blockY) * frameW + gx, 0u, 0u, 0u));
+    }
+};
+
 // MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK) k_primary(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
-                                                       CameraParams cam, uint32_t frameW, uint32_t blockY, uint32_t blockH,
-                                                       uint32_t seedsPerSample, int queueSlot) {
+                                                       const TraceParams *params, uint32_t seedsPerSample, int queueSlot) {
     __shared__ uint2 s_stack[MODE == 1 ? (TRAV_BLOCK / 32) * PC_STACK_SIZE : 1];
+    const CameraParams cam = params->cam;
+    const uint32_t frameW = params->frameW, blockY = params->blockY, blockH = params->blockH;
     const uint32_t n = frameW * blockH;
     const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->numRays[0] = (int)n;  // camera.cl:24-26
         atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
     }
-    const uint32_t tilesX = (frameW + 7) / 8, tilesY = (blockH + 3) / 4;
-    const uint32_t totalItems = MODE == 1 ? tilesX * tilesY * 32u : n;
     TravStats st{0, 0, 0};
     uint32_t missed = 0;
-    for (;;) {
-        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
-        if (unit >= totalItems) break;
-        uint32_t gx, gy;
-        bool valid;
-        if (MODE == 1) {
-            uint32_t tile = unit / 32u;
-            gx = (tile % tilesX) * 8u + (lane_id() & 7u);
-            gy = (tile / tilesX) * 4u + (lane_id() >> 3);
-            valid = gx < frameW && gy < blockH;
-        } else {
-            uint32_t i = unit + lane_id();
-            valid = i < n;
-            gx = i % frameW;
-            gy = i / frameW;
-        }
-        const uint32_t index = gy * frameW + gx;
-        float3 dir = f3(0.0f, 0.0f, 1.0f);
-        if (valid) {
-            dir = primaryRayDir(cam, gx, gy, blockY, randSeed);
-            fb.rays[0][index].origin = f4(cam.eye, FLT_MAX);  // rayNew (util/ray.cl:13-16)
-            fb.rays[0][index].dir = f4(dir, (float)index);
-            PathRec p;  // pathNew (util/path.cl:13-17)
-            p.throughput = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-            p.meta = make_uint4((gy + blockY) * frameW + gx, 0u, 0u, 0u);
-            fb.paths[index] = p;
-        }
-        Hit best;
-        int hit = 0;
-        if (MODE == 1) {
-            hit = traverse_packet<COUNT>(sc, s_stack + (threadIdx.x / 32) * PC_STACK_SIZE, valid, cam.eye, dir, FLT_MAX, best, st);
-        } else if (valid) {
-            hit = MODE == 2 ? traverseReference<false>(sc, cam.eye, dir, FLT_MAX, best)
-                            : traverse<false, COUNT>(sc, cam.eye, dir, FLT_MAX, best, st);
-        }
-        if (valid) {
-            fb.hitFlags[index] = (uint32_t)hit;
-            HitRec h;
-            h.wuvt = best.wuvt;
-            h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
-            fb.hits[index] = h;
-            if (COUNT && !hit) missed++;
+    if (MODE == 0) {
+        PrimarySource src{fb, cam, frameW, blockY, randSeed};
+        HitSink<COUNT> sink{fb.hitFlags, fb.hits, 0u};
+        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+        missed = sink.missed;
+    } else {
+        const uint32_t tilesX = (frameW + 7) / 8, tilesY = (blockH + 3) / 4;
+        const uint32_t totalItems = MODE == 1 ? tilesX * tilesY * 32u : n;
+        for (;;) {
+            uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+            if (unit >= totalItems) break;
+            uint32_t gx, gy;
+            bool valid;
+            if (MODE == 1) {
+                uint32_t tile = unit / 32u;
+                gx = (tile % tilesX) * 8u + (lane_id() & 7u);
+                gy = (tile / tilesX) * 4u + (lane_id() >> 3);
+                valid = gx < frameW && gy < blockH;
+            } else {
+                uint32_t i = unit + lane_id();
+                valid = i < n;
+                gx = i % frameW;
+                gy = i / frameW;
+            }
+            const uint32_t index = gy * frameW + gx;
+            float3 dir = f3(0.0f, 0.0f, 1.0f);
+            if (valid) {
+                dir = primaryRayDir(cam, gx, gy, blockY, randSeed);
+                st_ray(fb.rays[0] + index, f4(cam.eye, FLT_MAX), f4(dir, (float)index));  // rayNew (util/ray.cl:13-16)
+                // pathNew (util/path.cl:13-17)
+                __stcs(&fb.paths[index].throughput, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+                __stcs(&fb.paths[index].meta, make_uint4((gy + blockY) * frameW + gx, 0u, 0u, 0u));
+            }
+            Hit best;
+            int hit = 0;
+            if (MODE == 1) {
+                hit = traverse_packet<COUNT>(sc, s_stack + (threadIdx.x / 32) * PC_STACK_SIZE, valid, cam.eye, dir, FLT_MAX, best, st);
+            } else if (valid) {
+                hit = traverseReference<false>(sc, cam.eye, dir, FLT_MAX, best);
+            }
+            if (valid) {
+                __stcs(fb.hitFlags + index, (uint32_t)hit);
+                st_hit(fb.hits + index, best.wuvt, best.inst, best.tri);
+                if (COUNT && !hit) missed++;
+            }
         }
     }
     if (COUNT) {
@@ -268,27 +465,33 @@ __global__ void __launch_bounds__(TRAV_BLOCK) k_primary(DScene sc, FrameBufs fb,
 
 // rayIntersectionQuery over rays[a][0 .. numRays[a])
 template <bool REFERENCE, bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK) k_query(DScene sc, const Ray *rays, uint32_t *hitFlags, HitRec *hits,
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene sc, const Ray *rays, uint32_t *hitFlags, HitRec *hits,
                                                      TraceCtl *ctl, int a, int queueSlot) {
     const uint32_t n = (uint32_t)ctl->numRays[a];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
     TravStats st{0, 0, 0};
     uint32_t missed = 0;
-    for (;;) {
-        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
-        if (unit >= n) break;
-        uint32_t i = unit + lane_id();
-        if (i < n) {
-            float4 ro = rays[i].origin, rd = rays[i].dir;
-            Hit best;
-            int hit = REFERENCE ? traverseReference<false>(sc, xyz(ro), xyz(rd), ro.w, best)
-                                : traverse<false, COUNT>(sc, xyz(ro), xyz(rd), ro.w, best, st);
-            hitFlags[i] = (uint32_t)hit;
-            HitRec h;
-            h.wuvt = best.wuvt;
-            h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
-            hits[i] = h;
-            if (COUNT && !hit) missed++;
+    if (!REFERENCE) {
+        RaySource src{rays};
+        HitSink<COUNT> sink{hitFlags, hits, 0u};
+        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+        missed = sink.missed;
+    } else {
+        for (;;) {
+            uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+            if (unit >= n) break;
+            uint32_t i = unit + lane_id();
+            if (i < n) {
+                float4 ro = rays[i].origin, rd = rays[i].dir;
+                Hit best;
+                int hit = traverseReference<false>(sc, xyz(ro), xyz(rd), ro.w, best);
+                hitFlags[i] = (uint32_t)hit;
+                HitRec h;
+                h.wuvt = best.wuvt;
+                h.meta = make_uint4(best.inst, best.tri, 0u, 0u);
+                hits[i] = h;
+                if (COUNT && !hit) missed++;
+            }
         }
     }
     if (COUNT) {
@@ -302,32 +505,50 @@ __global__ void __launch_bounds__(TRAV_BLOCK) k_query(DScene sc, const Ray *rays
 // rayIntersectionTest over rays[2] + accumulateEmissiveSamples for the unoccluded ones.
 // At most one occlusion ray per path and bounce, so the accumulator update needs no atomic
 // (same argument as the reference, pt_integrator.cl:294-295).  hitFlags may be null.
+template <bool COUNT>
+struct OcclusionSink {
+    const Ray *rays;
+    const PathRec *paths;
+    const float4 *emissiveSamples;
+    float4 *acc;
+    uint32_t *hitFlags;
+    uint32_t unocc;
+    __device__ __forceinline__ void store(uint32_t i, int hit, const Trav &) {
+        if (hitFlags) hitFlags[i] = (uint32_t)hit;
+        if (!hit && acc) {
+            const uint32_t pathIndex = (uint32_t)__ldcs(&rays[i].dir.w);  // rayGetPathIndex (util/ray.cl:26-28)
+            const uint32_t pixel = paths[pathIndex].meta.x;
+            const float4 s = __ldcs(emissiveSamples + i);
+            float4 c = acc[pixel];
+            c.x += s.x; c.y += s.y; c.z += s.z;
+            acc[pixel] = c;
+            if (COUNT) unocc++;
+        }
+    }
+};
+
 template <bool REFERENCE, bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
                                                          const float4 *emissiveSamples, float4 *acc, uint32_t *hitFlags,
                                                          TraceCtl *ctl, int queueSlot) {
     const uint32_t n = (uint32_t)ctl->numRays[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)n);
     TravStats st{0, 0, 0};
-    uint32_t unocc = 0;
-    for (;;) {
-        uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
-        if (unit >= n) break;
-        uint32_t i = unit + lane_id();
-        if (i < n) {
-            float4 ro = rays[i].origin, rd = rays[i].dir;
-            Hit best;
-            int hit = REFERENCE ? traverseReference<true>(sc, xyz(ro), xyz(rd), ro.w, best)
-                                : traverse<true, COUNT>(sc, xyz(ro), xyz(rd), ro.w, best, st);
-            if (hitFlags) hitFlags[i] = (uint32_t)hit;
-            if (!hit && acc) {
-                uint32_t pathIndex = (uint32_t)rd.w;  // rayGetPathIndex (util/ray.cl:26-28)
-                uint32_t pixel = paths[pathIndex].meta.x;
-                float4 s = emissiveSamples[i];
-                float4 c = acc[pixel];
-                c.x += s.x; c.y += s.y; c.z += s.z;
-                acc[pixel] = c;
-                if (COUNT) unocc++;
+    OcclusionSink<COUNT> sink{rays, paths, emissiveSamples, acc, hitFlags, 0u};
+    if (!REFERENCE) {
+        RaySource src{rays};
+        trace_queue<true, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+    } else {
+        Trav dummy;
+        for (;;) {
+            uint32_t unit = next_unit(&ctl->queueHead[queueSlot]);
+            if (unit >= n) break;
+            uint32_t i = unit + lane_id();
+            if (i < n) {
+                float4 ro = rays[i].origin, rd = rays[i].dir;
+                Hit best;
+                int hit = traverseReference<true>(sc, xyz(ro), xyz(rd), ro.w, best);
+                sink.store(i, hit, dummy);
             }
         }
     }
@@ -335,7 +556,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) k_occlusion(DScene sc, const Ray *
         warp_add_stat(ctl, ST_NODES, st.nodes);
         warp_add_stat(ctl, ST_TRIS, st.tris);
         warp_add_stat(ctl, ST_INSTANCES, st.instances);
-        warp_add_stat(ctl, ST_UNOCCLUDED, unocc);
+        warp_add_stat(ctl, ST_UNOCCLUDED, sink.unocc);
     }
 }
 
@@ -409,13 +630,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         so.wantOcc = false; so.wantInd = false;
         float pathIndexF = 0.0f;
         if (i < n) {
-            const float4 rd = fb.rays[a][i].dir;
+            const float4 rd = __ldcs(&fb.rays[a][i].dir);
             pathIndexF = rd.w;
             const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
-            if (!fb.hitFlags[i]) {
+            if (!__ldcs(fb.hitFlags + i)) {
                 if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
                     float3 kd = shadeMiss(sc, xyz(rd));
-                    PathRec p = fb.paths[pathIndex];
+                    PathRec p = ld_path(fb.paths + pathIndex);
                     float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
                     float4 c = fb.traceAcc[p.meta.x];
                     c.x += add.x; c.y += add.y; c.z += add.z;
@@ -423,8 +644,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 }
             } else {
                 shaded++;
-                const HitRec h = fb.hits[i];
-                const PathRec p = fb.paths[pathIndex];
+                const HitRec h = ld_hit(fb.hits + i);
+                const PathRec p = ld_path(fb.paths + pathIndex);
                 shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, h.wuvt, h.meta.y, i, bounce, minBouncesForRR, randSeed, so);
                 if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
                 if (so.accum) {
@@ -442,8 +663,23 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         const unsigned ltMask = (1u << lane) - 1u;
         const uint32_t occTot = __popc(occMask), indTot = __popc(indMask);
         uint32_t occBase, indBase;
+#ifdef PC_EXPERIMENT_UNORDERED  // upper bound of what a wait-free compaction buys (results are NOT reproducible)
+        if (lane == 0) {
+            occBase = atomicAdd(&ctl->expCnt[bounce][0], occTot);
+            indBase = atomicAdd(&ctl->expCnt[bounce][1], indTot);
+            __threadfence();
+            if (atomicAdd(&ctl->expCnt[bounce][2], 1u) == nTiles - 1) {
+                ctl->numRays[2] = (int)atomicAdd(&ctl->expCnt[bounce][0], 0u);
+                ctl->numRays[1 - a] = (int)atomicAdd(&ctl->expCnt[bounce][1], 0u);
+            }
+        }
+        occBase = __shfl_sync(FULL, occBase, 0);
+        indBase = __shfl_sync(FULL, indBase, 0);
+        if (false) {
+#else
         lookback(status, ticket, occTot, indTot, occBase, indBase);
         if (ticket == nTiles - 1 && lane == 0) {  // the last tile publishes the queue lengths
+#endif
             ctl->numRays[2] = (int)(occBase + occTot);
             ctl->numRays[1 - a] = (int)(indBase + indTot);
             if (COUNT) {
@@ -453,14 +689,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         }
         if (so.wantOcc) {  // pt_integrator.cl:200-204
             const uint32_t k = occBase + __popc(occMask & ltMask);
-            fb.emissiveSamples[k] = f4(so.occSample, 0.0f);
-            fb.rays[2][k].origin = f4(so.occOrigin, so.occMaxDist);
-            fb.rays[2][k].dir = f4(so.occDir, pathIndexF);
+            __stcs(fb.emissiveSamples + k, f4(so.occSample, 0.0f));
+            st_ray(fb.rays[2] + k, f4(so.occOrigin, so.occMaxDist), f4(so.occDir, pathIndexF));
         }
         if (so.wantInd) {  // :207-210
             const uint32_t k = indBase + __popc(indMask & ltMask);
-            fb.rays[1 - a][k].origin = f4(so.indOrigin, FLT_MAX);
-            fb.rays[1 - a][k].dir = f4(so.indDir, pathIndexF);
+            st_ray(fb.rays[1 - a] + k, f4(so.indOrigin, FLT_MAX), f4(so.indDir, pathIndexF));
         }
     }
     if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);

@@ -169,6 +169,34 @@ def test_variants_bit_identical():
         assert (acc, cnt) == ref, f"variant {opts} differs"
 
 
+def test_sample_chains_equivalent():
+    """PC_OPT_SAMPLE_CHAINS only changes which samples overlap on the device: one sample is bit-identical for any
+    chain count, several samples differ from the single-chain result by float summation order alone, ray totals
+    are identical, and every chain count is deterministic."""
+    w = h = 160
+    sc = C.small_scene("c2", w, h)
+    spp = 7
+    seeds = T.splitmix_seeds(12, spp * 6)
+    res = {}
+    for chains in (1, 2, 3, 4, 8):
+        cu = C.cuda_for(sc, w, h, sample_chains=chains)
+        cu.trace(T.make_block_request(w, h, spp=1), seeds[:6])
+        one = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
+        runs = []
+        for _ in range(2):
+            cu.trace(T.make_block_request(w, h, spp=spp), seeds)
+            runs.append(cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).reshape(-1, 4)[:, :3].copy())
+        assert runs[0].tobytes() == runs[1].tobytes(), f"{chains} chains: not deterministic"
+        st = cu.stats().device
+        res[chains] = (one, runs[0], st["query_rays"], st["occlusion_rays"], cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32).tobytes())
+        cu.close()
+    for chains in (2, 3, 4, 8):
+        assert res[chains][0] == res[1][0], f"{chains} chains: a single sample must be bit-identical"
+        assert res[chains][2:] == res[1][2:], f"{chains} chains: ray totals / last-sample counters differ"
+        err = C.rel_err(res[chains][1], res[1][1])
+        assert err.max() <= 2e-6, f"{chains} chains: {err.max():.2e} beyond float summation order"
+
+
 def test_deterministic_and_progressive():
     w = h = 128
     sc = C.small_scene("c2", w, h)
@@ -345,4 +373,70 @@ def test_golden_bxdf_tables(key):
         fin = np.isfinite(a) & np.isfinite(b)
         err = np.abs(a - b)[fin] / np.maximum(np.abs(b)[fin], 1e-3)
         assert float((err > 1e-4).mean()) <= 2e-3, f
+    cu.close()
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE configs 3 and 4 at their REAL sizes (100k-triangle mesh x 1,000 instances at 1920x1080;
+# 10M-triangle terrain with textures and dispersion at 3840x2160).  The oracle cannot trace those frames
+# in seconds, but a block request IS the unit of work of the interface: a few rows of the real frame use
+# the real camera rays, the real two-level BVH and the real textures, and cost the oracle a second.
+# Config 4 needs a minute of scene compilation and ~6 GB of host memory, so it runs when POLARIS_FULL=1
+# (results of such a run are kept under profiles/).
+from polaris_b200 import scenes as _scenes  # noqa: E402
+
+_FULL = [("c3", "c3_instancing")] + ([("c4", "c4_terrain")] if os.environ.get("POLARIS_FULL") else [])
+
+
+@pytest.mark.parametrize("key,name", _FULL)
+def test_full_size_row_blocks(key, name):
+    w, h, _ = _scenes.CONFIGS[name]
+    sc = C.scene(name, w, h)
+    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h, counters=1)
+    seeds = T.splitmix_seeds(int(key[1]), 6)
+    checked = 0
+    for block_y, block_h in ((0, 4), (h // 2 - 2, 6), (h - 5, 5)):
+        n = w * block_h
+        rows = slice(block_y, block_y + block_h)
+        # one bounce: the block's primary rays are bit-exact, bounce-0 radiance within 1e-4
+        for tr in (orc, cu):
+            tr.trace(T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=1, num_bounces=1), seeds[:2])
+        assert cu.read_buffer(_lib.BUF_RAYS0, n, _lib.RAY_DTYPE).tobytes() == orc.read_buffer(_lib.BUF_RAYS0, n, _lib.RAY_DTYPE).tobytes()
+        _assert_close_pixels(C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h).reshape(h, w, 3)[rows].reshape(-1, 3),
+                             C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h).reshape(h, w, 3)[rows].reshape(-1, 3), 1e-4, f"{key} bounce 0")
+        # full depth
+        ro = T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=1)
+        rg = T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=1)
+        orc.trace(ro, seeds)
+        cu.trace(rg, seeds)
+        g = C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h).reshape(h, w, 3)
+        o = C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h).reshape(h, w, 3)
+        _assert_close_pixels(g[rows].reshape(-1, 3), o[rows].reshape(-1, 3), 1e-3, f"{key} rows {block_y}..{block_y + block_h}")
+        outside = np.ones(h, bool)
+        outside[rows] = False
+        assert g[outside].sum() == 0  # radiance stays inside the block's rows (SURVEY Q4 fixed)
+        so, sg = orc.stats().device, cu.stats().device
+        for k in ("query_rays", "occlusion_rays", "shaded_hits", "missed_query_rays"):
+            assert abs(so[k] - sg[k]) <= max(4, int(1e-3 * so[k])), (k, so[k], sg[k])
+        checked += n
+    # hit records on rays of the last block (primary + bounce + occlusion), all three traversal modes
+    cnt = orc.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32)
+    rays = np.concatenate([orc.read_buffer(_lib.BUF_RAYS0, w * h, _lib.RAY_DTYPE)[: min(cnt[0], 4096)],
+                           orc.read_buffer(_lib.BUF_RAYS1, w * h, _lib.RAY_DTYPE)[: min(cnt[1], 4096)],
+                           orc.read_buffer(_lib.BUF_RAYS2, w * h, _lib.RAY_DTYPE)[: min(cnt[2], 2048)]]).copy()
+    rng = np.random.default_rng(1)
+    extra = orc.read_buffer(_lib.BUF_RAYS0, w * 4, _lib.RAY_DTYPE).copy()  # leftovers of an earlier bounce are rays too
+    rays = np.concatenate([rays, extra[rng.choice(len(extra), 2048, replace=False)]])
+    rays = rays[np.isfinite(rays["dir"][:, :3]).all(axis=1) & (np.abs(rays["dir"][:, :3]).sum(axis=1) > 0)]
+    of, oh = orc.debug_intersect(rays, 0)
+    hit = of == 1
+    for label, mode, ref_order in (("per-ray", 0, 0), ("packet", 2, 0), ("reference-order", 0, 1)):
+        cu.set_option(_lib.OPT_REFERENCE_ORDER, ref_order)
+        gf, gh = cu.debug_intersect(rays, mode)
+        assert np.array_equal(gf, of), f"{key} {label}"
+        assert np.array_equal(gh["mesh_instance"][hit], oh["mesh_instance"][hit]) and np.array_equal(gh["tri_index"][hit], oh["tri_index"][hit]), f"{key} {label}"
+        assert gh["wuvt"][hit].tobytes() == oh["wuvt"][hit].tobytes(), f"{key} {label}"
+    cu.set_option(_lib.OPT_REFERENCE_ORDER, 0)
+    print(f"{key}: {checked} pixels in 3 row blocks of the {w}x{h} frame, {len(rays)} rays ({int(hit.sum())} hits) checked; "
+          f"{sc.num_triangles} triangles x {len(sc.mesh_instances)} instances")
     cu.close()

@@ -1,4 +1,8 @@
-for v in "" ab_inline.so ab_mb3.so ab_mb5.so ab_mb6.so ab_mb8.so; do
-  echo "== variant ${v:-default}"
-  POLARIS_CUDA_LIB=${v:+$PWD/$v} timeout 200 python bench.py --steps 2 --warmup 1 --spp 64 --no-cpu 2>&1 | grep -E "timed|kernel classes" | sed -e 's/"alg_GBps": [0-9.]*//g' | cut -c1-420
+#!/bin/bash
+# A/B timing of library variants on ONE GPU: tools/ab.sh name1 name2 ...  (ab_<name>.so at the repo root,
+# "default" = polaris_b200/libpolaris_cuda.so).  Prints the timed line and the per-kernel-class table.
+for v in "$@"; do
+  echo "== variant $v"
+  lib=""; [ "$v" != default ] && lib=$PWD/ab_$v.so
+  POLARIS_CUDA_LIB=$lib timeout 300 python bench.py --steps 2 --warmup 2 --spp ${AB_SPP:-64} --no-cpu 2>&1 | grep -E "timed|kernel classes|Error|error" | sed -e 's/"alg_GBps": [0-9.]*//g' -e 's/"launches": [0-9]*, //g' | cut -c1-420
 done
