@@ -249,6 +249,9 @@ def run_cuda_single(args):
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
     if args.chains:
         tr.set_option(_lib.OPT_SAMPLE_CHAINS, args.chains)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        tr.set_option(getattr(_lib, "OPT_" + k.upper()), int(v))
 
     def frame(e2e=False):
         if e2e:  # host scene buffers -> device, every step
@@ -510,6 +513,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
     ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")
+    ap.add_argument("--opt", action="append", default=[], help="NAME=VALUE tracer option, e.g. PRIMARY_PACKETS=0 (experiments)")
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="N=1 only: BASELINE config to run (default c2 = configs[1], the one the metric is quoted on)")
     args = ap.parse_args()

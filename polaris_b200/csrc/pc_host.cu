@@ -410,7 +410,7 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     if (perSM > 8) perSM = 8;
     tr->persistentGrid = tr->prop.multiProcessorCount * perSM;
     int shadePerSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
     if (shadePerSM < 1) shadePerSM = 1;
     tr->shadeGrid = tr->prop.multiProcessorCount * shadePerSM;
     tr->sc.sceneDiffuseMat = -1;

@@ -8,10 +8,11 @@
 //                   warp-packet traversal (shared stack + votes, the Guenther et al. scheme the
 //                   reference uses on GPUs, intersect.cl:353-575) or per-ray traversal
 //   k_shade         shadePrimaryRayMisses / shadeIndirectRayMisses + shadeHits
-//                   (pt_integrator.cl:17-275) with STABLE compaction of the occlusion and
-//                   indirect rays: warp ballot + popc prefix inside a 32-ray tile and a single-pass
-//                   decoupled look-back across tiles (ticket ordered), so ray order == parent ray
-//                   order, which is what makes bounce >= 1 reproducible
+//                   (pt_integrator.cl:17-275): 256-ray CTA tiles sorted by material, then STABLE
+//                   compaction of the occlusion and indirect rays (ballot + popc per warp, offsets
+//                   across the CTA, a single-pass decoupled look-back across tiles, ticket ordered),
+//                   so ray order == parent ray order, which is what makes bounce >= 1 reproducible
+//                   
 //   k_occlusion     rayIntersectionTest + accumulateEmissiveSamples (intersect.cl:26-180,
 //                   pt_integrator.cl:278-296)
 //   k_query         rayIntersectionQuery (intersect.cl:184-347) for the indirect rays
@@ -28,9 +29,12 @@ namespace pc {
 
 constexpr int MAX_BOUNCES = 32;
 constexpr int TRAV_BLOCK = 128;   // 4 warps
-constexpr int SHADE_BLOCK = 128;  // 4 warps
+#ifndef PC_SHADE_BLOCK
+#define PC_SHADE_BLOCK 256
+#endif
+constexpr int SHADE_BLOCK = PC_SHADE_BLOCK;
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 6
+#define SHADE_MIN_BLOCKS 3
 #endif
 #ifndef PC_TRAV_MIN_BLOCKS
 #define PC_TRAV_MIN_BLOCKS 8
@@ -51,7 +55,6 @@ struct TraceCtl {
     unsigned long long stats[ST_COUNT];  // [persist]
     uint32_t queueHead[2 * MAX_BOUNCES + 2];  // [sample] work-queue heads, one per traversal launch
     uint32_t ticket[MAX_BOUNCES];             // [sample] block tickets of the shade launches
-    uint32_t expCnt[MAX_BOUNCES][3];          // [sample] PC_EXPERIMENT_UNORDERED only
 };
 
 // Per-pc_trace parameters that change from block to block or frame to frame (camera moves, the
@@ -111,7 +114,7 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
         ctl->nextSample = ctl->nextSample + sampleStride;
     }
     if (i < 2 * MAX_BOUNCES + 2) ctl->queueHead[i] = 0;
-    if (i < MAX_BOUNCES) { ctl->ticket[i] = 0; ctl->expCnt[i][0] = 0; ctl->expCnt[i][1] = 0; ctl->expCnt[i][2] = 0; }
+    if (i < MAX_BOUNCES) ctl->ticket[i] = 0;
     for (size_t k = i; k < statusWords; k += stride) status[k] = 0ull;
 }
 
@@ -604,28 +607,101 @@ __device__ __forceinline__ void lookback(volatile unsigned long long *status, ui
     if (lane == 0) status[ticket] = pack_status(2ull, accO + occTot, accI + indTot);
 }
 
-// shadePrimaryRayMisses / shadeIndirectRayMisses / shadeHits for rays[a][0 .. numRays[a]).
-// Persistent: every warp pulls 32-ray tiles by ticket until none are left; no block-wide barrier.
+// ------------------------------------------------------------------------------------------------
+// k_shade: shadePrimaryRayMisses / shadeIndirectRayMisses / shadeHits for rays[a][0 .. numRays[a]),
+// persistent over CTA tiles of SHADE_BLOCK consecutive rays handed out by ticket.
+//
+// A warp that simply shades 32 consecutive rays meets up to six different materials (plus misses) and
+// executes every BxDF / light / texture path present one after the other: measured on config 2 (ncu,
+// profiles/) 13 of 32 lanes were active and 26 % of the stalls were instruction fetch (100 KB of shading
+// code wanted by all warps all the time).  Sorting the tile by material first executes 38 % fewer warp
+// instructions; 256-ray tiles beat 128 (purer warps) and 512 (too few resident CTAs).
+//   1. each thread reads the (hit flag, triangle) of its ray and takes the triangle's material root
+//      as sort key; a counting sort over the CTA (warp match + a 256-entry histogram scan in shared
+//      memory) yields a permutation that groups equal materials;
+//   2. thread t shades ray perm[t]: warps now hold (mostly) one material each;
+//   3. results are staged in shared memory at the ray's ORIGINAL slot, compacted in original order
+//      (ballot + popc per warp, offsets across the CTA, ONE decoupled look-back per CTA tile) and
+//      written out -- the output order is parent ray order, whichever lane did the arithmetic for a ray.
+// ------------------------------------------------------------------------------------------------
+constexpr int SHADE_WARPS = SHADE_BLOCK / 32;
+constexpr int SHADE_KEYS = 64;  // histogram bins: material roots modulo 62, misses, inactive lanes
+constexpr uint32_t KEY_MISS = SHADE_KEYS - 2, KEY_INACTIVE = SHADE_KEYS - 1;
+
+struct ShadeShared {
+    float occ[10][SHADE_BLOCK];   // origin.xyz, maxDist, dir.xyz, sample.xyz   (struct of arrays: conflict free)
+    float ind[6][SHADE_BLOCK];    // origin.xyz, dir.xyz
+    float pathIndexF[SHADE_BLOCK];
+    uint32_t hitTri[SHADE_BLOCK];  // triangle of the hit, 0xFFFFFFFF for a miss
+    uint32_t hist[SHADE_KEYS * SHADE_WARPS];
+    uint16_t perm[SHADE_BLOCK];
+    uint8_t flags[SHADE_BLOCK];    // bit 0 occlusion ray wanted, bit 1 indirect ray wanted
+    uint32_t warpOcc[SHADE_WARPS], warpInd[SHADE_WARPS];
+    uint32_t tile, occBase, indBase;
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                       unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
                                                       uint32_t minBouncesForRR, int a, int fixQ4) {
+    __shared__ ShadeShared sh;
     const unsigned FULL = 0xFFFFFFFFu;
-    const unsigned lane = lane_id();
+    const unsigned lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t n = (uint32_t)ctl->numRays[a];
-    const uint32_t nTiles = (n + 31u) / 32u;
-    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) {  // resources.go:230-238: both counters reset
+    const uint32_t nTiles = (n + SHADE_BLOCK - 1u) / SHADE_BLOCK;
+    if (n == 0 && blockIdx.x == 0 && tid == 0) {  // resources.go:230-238: both counters reset
         ctl->numRays[2] = 0;
         ctl->numRays[1 - a] = 0;
     }
     const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample + 1 + bounce];
     uint32_t shaded = 0;
     for (;;) {
-        uint32_t ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&ctl->ticket[bounce], 1u);
-        ticket = __shfl_sync(FULL, ticket, 0);
-        if (ticket >= nTiles) break;
-        const uint32_t i = ticket * 32u + lane;
+        __syncthreads();  // the previous tile's shared state is no longer in use
+        if (tid == 0) sh.tile = atomicAdd(&ctl->ticket[bounce], 1u);
+        for (int k = tid; k < SHADE_KEYS * SHADE_WARPS; k += SHADE_BLOCK) sh.hist[k] = 0u;
+        __syncthreads();
+        const uint32_t tile = sh.tile;
+        if (tile >= nTiles) break;
+        const uint32_t base = tile * SHADE_BLOCK;
+        // ---- 1. sort key of my own ray
+        uint32_t key = KEY_INACTIVE;
+        {
+            const uint32_t i = base + tid;
+            uint32_t tri = 0xFFFFFFFFu;
+            if (i < n) {
+                key = KEY_MISS;
+                if (__ldcs(fb.hitFlags + i)) {
+                    tri = __ldcs(&fb.hits[i].meta).y;
+                    key = PC_LDG(sc.matIndex + tri) % (uint32_t)(SHADE_KEYS - 2);
+                }
+            }
+            sh.hitTri[tid] = tri;
+        }
+        const unsigned peers = __match_any_sync(FULL, key);
+        if (lane == (unsigned)(__ffs((int)peers) - 1)) sh.hist[key * SHADE_WARPS + warp] = (uint32_t)__popc(peers);
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the (key major, warp minor) histogram: 8 entries per lane
+            constexpr int PER = SHADE_KEYS * SHADE_WARPS / 32;
+            uint32_t v[PER], sum = 0;
+#pragma unroll
+            for (int k = 0; k < PER; k++) { v[k] = sh.hist[lane * PER + k]; sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < PER; k++) { sh.hist[lane * PER + k] = run; run += v[k]; }
+        }
+        __syncthreads();
+        sh.perm[sh.hist[key * SHADE_WARPS + warp] + (uint32_t)__popc(peers & ltMask)] = (uint16_t)tid;
+        __syncthreads();
+        // ---- 2. shade ray perm[tid]
+        const uint32_t slot = sh.perm[tid];
+        const uint32_t i = base + slot;
         ShadeOut so;
         so.wantOcc = false; so.wantInd = false;
         float pathIndexF = 0.0f;
@@ -633,7 +709,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             const float4 rd = __ldcs(&fb.rays[a][i].dir);
             pathIndexF = rd.w;
             const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
-            if (!__ldcs(fb.hitFlags + i)) {
+            const uint32_t tri = sh.hitTri[slot];
+            if (tri == 0xFFFFFFFFu) {
                 if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
                     float3 kd = shadeMiss(sc, xyz(rd));
                     PathRec p = ld_path(fb.paths + pathIndex);
@@ -644,9 +721,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 }
             } else {
                 shaded++;
-                const HitRec h = ld_hit(fb.hits + i);
+                const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
                 const PathRec p = ld_path(fb.paths + pathIndex);
-                shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, h.wuvt, h.meta.y, i, bounce, minBouncesForRR, randSeed, so);
+                shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, i, bounce, minBouncesForRR, randSeed, so);
                 if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
                 if (so.accum) {
                     const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
@@ -657,44 +734,59 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
             }
         }
-        // ---- stable compaction (replaces the local/global atomics of pt_integrator.cl:162,176,188-197):
-        // ballot + popc inside the tile, decoupled look-back across tiles
-        const unsigned occMask = __ballot_sync(FULL, so.wantOcc), indMask = __ballot_sync(FULL, so.wantInd);
-        const unsigned ltMask = (1u << lane) - 1u;
-        const uint32_t occTot = __popc(occMask), indTot = __popc(indMask);
-        uint32_t occBase, indBase;
-#ifdef PC_EXPERIMENT_UNORDERED  // upper bound of what a wait-free compaction buys (results are NOT reproducible)
-        if (lane == 0) {
-            occBase = atomicAdd(&ctl->expCnt[bounce][0], occTot);
-            indBase = atomicAdd(&ctl->expCnt[bounce][1], indTot);
-            __threadfence();
-            if (atomicAdd(&ctl->expCnt[bounce][2], 1u) == nTiles - 1) {
-                ctl->numRays[2] = (int)atomicAdd(&ctl->expCnt[bounce][0], 0u);
-                ctl->numRays[1 - a] = (int)atomicAdd(&ctl->expCnt[bounce][1], 0u);
+        // ---- 3. stage at the ORIGINAL slot
+        sh.flags[slot] = (uint8_t)((so.wantOcc ? 1u : 0u) | (so.wantInd ? 2u : 0u));
+        sh.pathIndexF[slot] = pathIndexF;
+        if (so.wantOcc) {
+            sh.occ[0][slot] = so.occOrigin.x; sh.occ[1][slot] = so.occOrigin.y; sh.occ[2][slot] = so.occOrigin.z;
+            sh.occ[3][slot] = so.occMaxDist;
+            sh.occ[4][slot] = so.occDir.x; sh.occ[5][slot] = so.occDir.y; sh.occ[6][slot] = so.occDir.z;
+            sh.occ[7][slot] = so.occSample.x; sh.occ[8][slot] = so.occSample.y; sh.occ[9][slot] = so.occSample.z;
+        }
+        if (so.wantInd) {
+            sh.ind[0][slot] = so.indOrigin.x; sh.ind[1][slot] = so.indOrigin.y; sh.ind[2][slot] = so.indOrigin.z;
+            sh.ind[3][slot] = so.indDir.x; sh.ind[4][slot] = so.indDir.y; sh.ind[5][slot] = so.indDir.z;
+        }
+        __syncthreads();
+        // ---- 4. stable compaction in original order (replaces pt_integrator.cl:162,176,188-197)
+        const uint32_t f = sh.flags[tid];
+        const unsigned occMask = __ballot_sync(FULL, (f & 1u) != 0u), indMask = __ballot_sync(FULL, (f & 2u) != 0u);
+        if (lane == 0) { sh.warpOcc[warp] = (uint32_t)__popc(occMask); sh.warpInd[warp] = (uint32_t)__popc(indMask); }
+        __syncthreads();
+        uint32_t occOff = 0, indOff = 0, occTot = 0, indTot = 0;
+#pragma unroll
+        for (int wv = 0; wv < SHADE_WARPS; wv++) {
+            const uint32_t o = sh.warpOcc[wv], q = sh.warpInd[wv];
+            if (wv < (int)warp) { occOff += o; indOff += q; }
+            occTot += o; indTot += q;
+        }
+        if (warp == 0) {
+            uint32_t occBase, indBase;
+            lookback(status, tile, occTot, indTot, occBase, indBase);
+            if (lane == 0) {
+                sh.occBase = occBase; sh.indBase = indBase;
+                if (tile == nTiles - 1) {  // the last tile publishes the queue lengths
+                    ctl->numRays[2] = (int)(occBase + occTot);
+                    ctl->numRays[1 - a] = (int)(indBase + indTot);
+                    if (COUNT) {
+                        atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(occBase + occTot));
+                        atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(indBase + indTot));
+                    }
+                }
             }
         }
-        occBase = __shfl_sync(FULL, occBase, 0);
-        indBase = __shfl_sync(FULL, indBase, 0);
-        if (false) {
-#else
-        lookback(status, ticket, occTot, indTot, occBase, indBase);
-        if (ticket == nTiles - 1 && lane == 0) {  // the last tile publishes the queue lengths
-#endif
-            ctl->numRays[2] = (int)(occBase + occTot);
-            ctl->numRays[1 - a] = (int)(indBase + indTot);
-            if (COUNT) {
-                atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(occBase + occTot));
-                atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(indBase + indTot));
-            }
+        __syncthreads();
+        const float pif = sh.pathIndexF[tid];
+        if (f & 1u) {  // pt_integrator.cl:200-204
+            const uint32_t k = sh.occBase + occOff + (uint32_t)__popc(occMask & ltMask);
+            __stcs(fb.emissiveSamples + k, make_float4(sh.occ[7][tid], sh.occ[8][tid], sh.occ[9][tid], 0.0f));
+            st_ray(fb.rays[2] + k, make_float4(sh.occ[0][tid], sh.occ[1][tid], sh.occ[2][tid], sh.occ[3][tid]),
+                   make_float4(sh.occ[4][tid], sh.occ[5][tid], sh.occ[6][tid], pif));
         }
-        if (so.wantOcc) {  // pt_integrator.cl:200-204
-            const uint32_t k = occBase + __popc(occMask & ltMask);
-            __stcs(fb.emissiveSamples + k, f4(so.occSample, 0.0f));
-            st_ray(fb.rays[2] + k, f4(so.occOrigin, so.occMaxDist), f4(so.occDir, pathIndexF));
-        }
-        if (so.wantInd) {  // :207-210
-            const uint32_t k = indBase + __popc(indMask & ltMask);
-            st_ray(fb.rays[1 - a] + k, f4(so.indOrigin, FLT_MAX), f4(so.indDir, pathIndexF));
+        if (f & 2u) {  // :207-210
+            const uint32_t k = sh.indBase + indOff + (uint32_t)__popc(indMask & ltMask);
+            st_ray(fb.rays[1 - a] + k, make_float4(sh.ind[0][tid], sh.ind[1][tid], sh.ind[2][tid], FLT_MAX),
+                   make_float4(sh.ind[3][tid], sh.ind[4][tid], sh.ind[5][tid], pif));
         }
     }
     if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);
