@@ -37,7 +37,9 @@ constexpr uint32_t REF_LEAF = 0x80000000u;
 constexpr uint32_t REF_TOP = 0x40000000u;
 constexpr uint32_t REF_POP_INSTANCE = 0xFFFFFFFFu;  // stack marker: restore the world-space ray
 constexpr uint32_t REF_DONE = 0xFFFFFFFEu;          // traversal finished (never stored)
+constexpr uint32_t REF_POP_TRANSLATED = 0xFFFFFFFDu;  // stack marker: restore the origin only (translation-only instance)
 constexpr uint32_t INST_FLAG_IDENTITY = 1u;
+constexpr uint32_t INST_FLAG_TRANSLATION = 2u;
 
 // bxdf.cl:10-21, material_sampler.cl:4-9, path.cl:4-6, emissive_sampler.cl:4-5, texture_sampler.cl:4-7
 constexpr uint32_t BXDF_INVALID = 0, BXDF_EMISSIVE = 2, BXDF_DIFFUSE = 4, BXDF_CONDUCTOR = 8,
@@ -764,9 +766,12 @@ PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
 // Returns 0 to continue, 1 when the walk is over.  Requires bits 31:30 == 11 and cur != REF_DONE.
 template <bool COUNT>
 PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
-    if (t.cur == REF_POP_INSTANCE) {
-        t.o = t.o0; t.d = t.d0;
-        t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
+    if (t.cur == REF_POP_INSTANCE || t.cur == REF_POP_TRANSLATED) {
+        t.o = t.o0;
+        if (t.cur == REF_POP_INSTANCE) {
+            t.d = t.d0;
+            t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
+        }
         if (t.sp == 0) return 1;
         t.cur = stack[--t.sp];
         return 0;
@@ -776,7 +781,15 @@ PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
     const float4 *ip = sc.inst80 + 5 * (size_t)t.curInst;
     float4 hdr = PC_LDG(ip);
     t.curRank = f2u(hdr.z);
-    if (!(f2u(hdr.y) & INST_FLAG_IDENTITY)) {
+    const uint32_t iflags = f2u(hdr.y);
+    if (iflags & INST_FLAG_TRANSLATION) {
+        // translation only: mul4x1 is x*1 + y*0 + z*0 + t == x + t and mul3x1 leaves the direction (and
+        // therefore 1/d) untouched, exactly, for finite inputs -- one 16 B load instead of four and no
+        // reciprocals on the way in or out
+        float4 m3 = PC_LDG(ip + 4);
+        t.o = f3(t.o.x + m3.x, t.o.y + m3.y, t.o.z + m3.z);
+        stack[t.sp++] = REF_POP_TRANSLATED;
+    } else if (!(iflags & INST_FLAG_IDENTITY)) {
         // identity matrices are skipped: x*1 + y*0 + z*0 + 0 == x exactly for finite inputs
         float4 m0 = PC_LDG(ip + 1), m1 = PC_LDG(ip + 2), m2 = PC_LDG(ip + 3), m3 = PC_LDG(ip + 4);
         t.o = mul4x1(t.o, m0, m1, m2, m3);

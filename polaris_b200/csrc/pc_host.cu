@@ -99,7 +99,8 @@ struct pc_tracer {
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 1, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4;
+    int occGrid = 0;
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
     std::vector<int> timerClass;
@@ -231,9 +232,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
         if (tr->optRefOrder)
-            k_occlusion<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
         else
-            k_occlusion<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
         }
         L++;
         slot++;
@@ -407,10 +408,15 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     int perSM = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_query<false, false>, TRAV_BLOCK, 0);
     if (perSM < 1) perSM = 1;
-    if (perSM > 8) perSM = 8;
+    if (perSM > 16) perSM = 16;
     tr->persistentGrid = tr->prop.multiProcessorCount * perSM;
+    int occPerSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occPerSM, k_occlusion<false, false>, TRAV_BLOCK, 0);
+    if (occPerSM < 1) occPerSM = 1;
+    if (occPerSM > 16) occPerSM = 16;
+    tr->occGrid = tr->prop.multiProcessorCount * occPerSM;
     int shadePerSM = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
     if (shadePerSM < 1) shadePerSM = 1;
     tr->shadeGrid = tr->prop.multiProcessorCount * shadePerSM;
     tr->sc.sceneDiffuseMat = -1;

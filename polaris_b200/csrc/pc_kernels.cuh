@@ -39,6 +39,9 @@ constexpr int SHADE_BLOCK = PC_SHADE_BLOCK;
 #ifndef PC_TRAV_MIN_BLOCKS
 #define PC_TRAV_MIN_BLOCKS 8
 #endif
+#ifndef PC_OCC_MIN_BLOCKS
+#define PC_OCC_MIN_BLOCKS PC_TRAV_MIN_BLOCKS
+#endif
 
 enum StatIdx {
     ST_QUERY_RAYS = 0, ST_OCCLUSION_RAYS, ST_NODES, ST_TRIS, ST_INSTANCES, ST_SHADED, ST_OCC_EMITTED,
@@ -531,7 +534,7 @@ struct OcclusionSink {
 };
 
 template <bool REFERENCE, bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
                                                          const float4 *emissiveSamples, float4 *acc, uint32_t *hitFlags,
                                                          TraceCtl *ctl, int queueSlot) {
     const uint32_t n = (uint32_t)ctl->numRays[2];

@@ -51,6 +51,7 @@ constexpr uint32_t REF_LEAF = 0x80000000u;
 constexpr uint32_t REF_TOP = 0x40000000u;
 constexpr uint32_t REF_POP_INSTANCE = 0xFFFFFFFFu;  // stack marker, never stored in a node
 constexpr uint32_t INST_FLAG_IDENTITY = 1u;
+constexpr uint32_t INST_FLAG_TRANSLATION = 2u;  // linear part is the identity: only the origin moves
 
 inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
@@ -111,9 +112,12 @@ class Builder {
             bool ident = true;
             static const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
             for (int k = 0; k < 16; k++) ident = ident && (ri.m[k] == I[k]);
+            bool transl = true;  // columns 0-2 and the last row are the identity's (column-major, matrix.go:61-69)
+            for (int k = 0; k < 12; k++) transl = transl && (ri.m[k] == I[k]);
+            transl = transl && ri.m[15] == 1.0f;
             Q *q = &L.inst80[5 * i];
             q[0].x = u2f(root_ref);
-            q[0].y = u2f(ident ? INST_FLAG_IDENTITY : 0u);
+            q[0].y = u2f(ident ? INST_FLAG_IDENTITY : (transl ? INST_FLAG_TRANSLATION : 0u));
             q[0].z = u2f(inst_rank_.count((uint32_t)i) ? inst_rank_[(uint32_t)i] : 0xFFFFFFu);
             q[0].w = u2f(ri.mesh_index);
             for (int c = 0; c < 4; c++) q[1 + c] = Q{ri.m[4 * c], ri.m[4 * c + 1], ri.m[4 * c + 2], ri.m[4 * c + 3]};

@@ -292,7 +292,7 @@ extern "C" int pe_simt(void *h, const void *rays_in, uint32_t n, int anyHit, int
     TravStats st{0, 0, 0};
     auto isTri = [](uint32_t c) { return (c & REF_LEAF) && !(c & REF_TOP) && c != REF_POP_INSTANCE && c != REF_DONE; };
     auto isIdentityInst = [&](uint32_t c) {
-        if (!((c & REF_LEAF) && (c & REF_TOP)) || c == REF_POP_INSTANCE || c == REF_DONE) return false;
+        if (!((c & REF_LEAF) && (c & REF_TOP)) || c >= REF_POP_TRANSLATED) return false;
         uint32_t id = c & 0x3FFFFFFFu;
         return (f2u(sc.inst80[5 * (size_t)id].y) & INST_FLAG_IDENTITY) != 0;
     };
