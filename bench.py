@@ -320,7 +320,7 @@ def run_cuda_single(args):
     achieved = by[dom] / max(1, times[dom])  # bytes per ns == GB/s
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == "c2":  # the ncu capture was taken on config 2
         try:
             traffic = json.load(open(tp)).get(dom)
         except Exception:

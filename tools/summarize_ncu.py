@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Summarise gpurun_out/prof_<kernel>_<round>.ncu-rep + launches_<round>.csv into profiles/ (tracked):
+   profiles/ncu_<round>_summary.md, profiles/launches_<round>.csv, profiles/traffic.json (bench.py reads it).
+   python tools/summarize_ncu.py r01c"""
+import csv, json, os, subprocess, sys, collections
+
+R = sys.argv[1]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed.avg.per_cycle_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "l1tex__t_sector_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct", "sm__sass_branch_targets_threads_divergent.sum",
+        "smsp__sass_average_branch_targets_threads_uniform.pct", "launch__grid_size", "launch__block_size"]
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return rows[0], rows[1], rows[2:]
+
+
+md = [f"# ncu summary {R} (bench.py --steps 1 --warmup 1 --spp 4 --chains 1, config 2, one B200)\n",
+      "`--set full --clock-control none --import-source on`, two launches per kernel class (skip 6).  Durations under ncu are",
+      "cold-cache and serialised: compare shares, not absolutes.  dram bytes are per launch.\n"]
+traffic = {}
+for k in ("k_shade", "k_query", "k_occlusion", "k_primary"):
+    rep = os.path.join(G, f"prof_{k}_{R}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    hdr, units, rows = raw(rep)
+    md.append(f"## {k}\n")
+    md.append("| metric | unit | launch 1 | launch 2 |")
+    md.append("|---|---|---|---|")
+    vals = []
+    for key in KEYS:
+        if key in hdr:
+            i = hdr.index(key)
+            md.append(f"| {key} | {units[i]} | " + " | ".join(r[i] for r in rows[:2]) + " |")
+    stall = collections.OrderedDict()
+    for i, h in enumerate(hdr):
+        if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+            try:
+                stall[h.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(rows[0][i])
+            except ValueError:
+                pass
+    tot = sum(stall.values()) or 1
+    md.append("\nstall reasons (launch 1): " + ", ".join(f"{h} {100*v/tot:.0f}%" for h, v in sorted(stall.items(), key=lambda kv: -kv[1])[:8]) + "\n")
+    try:
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tb = [float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1) for r in rows[:2]]
+        traffic[k] = sum(tb) / len(tb)
+    except Exception:
+        pass
+os.makedirs(P, exist_ok=True)
+open(os.path.join(P, f"ncu_{R}_summary.md"), "w").write("\n".join(md) + "\n")
+src = os.path.join(G, f"launches_{R}.csv")
+if os.path.exists(src):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 14 and r[0].isdigit()]
+    tot = collections.defaultdict(float); cnt = collections.Counter()
+    for r in rows:
+        name = r[4].split("(")[0].replace("void ", "")
+        tot[name] += float(r[14]); cnt[name] += 1
+    s = sum(tot.values())
+    with open(os.path.join(P, f"launches_{R}.csv"), "w") as f:
+        f.write("kernel,launches,total_ns,share,avg_ns\n")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+            f.write(f"{k},{cnt[k]},{v:.0f},{v/s:.4f},{v/cnt[k]:.0f}\n")
+if traffic:
+    traffic["_note"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, {R}, config 2 at 4 spp"
+    json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+print("\n".join(md[:12]))
+print(traffic)
