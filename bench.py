@@ -309,10 +309,18 @@ def run_cuda_single(args):
     times = {n: st["kernel_time_ns"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
     counts = {n: st["kernel_count"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
     total_ns = sum(times.values())
-    dom = max(("k_primary", "k_shade", "k_occlusion", "k_query"), key=lambda k: times[k])
+    if counts.get("k_trace"):
+        # PC_OPT_FUSE_TRACE: the occlusion test and the next bounce's query share a launch, and the device
+        # counters are per trace call, not per launch: report the two traversal classes as one ("k_trace" =
+        # the fused launches + the last bounce's stand-alone k_occlusion)
+        by["k_trace"] = by.pop("k_query") + by.pop("k_occlusion")
+        times["k_trace"] += times.pop("k_query") + times.pop("k_occlusion")
+        counts["k_trace"] += counts.pop("k_query") + counts.pop("k_occlusion")
+    classes = [k for k in ("k_primary", "k_shade", "k_occlusion", "k_query", "k_trace") if counts.get(k)]
+    dom = max(classes, key=lambda k: times[k])
     peak, peak_src = measured_hbm_peak()
     kern = {}
-    for k in ("k_primary", "k_shade", "k_occlusion", "k_query"):
+    for k in classes:
         if counts[k]:
             kern[k] = {"launches": counts[k], "avg_us": times[k] / counts[k] / 1e3, "share": times[k] / max(1, total_ns),
                        "alg_GBps": by[k] / max(1, times[k])}

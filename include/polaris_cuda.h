@@ -90,7 +90,8 @@ typedef struct pc_stats {
 } pc_stats;
 
 typedef enum pc_kernel_class {
-    PC_K_BEGIN_SAMPLE = 0, PC_K_PRIMARY = 1, PC_K_SHADE = 2, PC_K_OCCLUSION = 3, PC_K_QUERY = 4
+    PC_K_BEGIN_SAMPLE = 0, PC_K_PRIMARY = 1, PC_K_SHADE = 2, PC_K_OCCLUSION = 3, PC_K_QUERY = 4,
+    PC_K_TRACE = 5   /* occlusion test + next bounce's closest-hit query in one launch (PC_OPT_FUSE_TRACE) */
 } pc_kernel_class;
 
 /* scene.Scene flat buffers, reference asset/scene/optimized_scene.go:167-190, in the
@@ -136,12 +137,15 @@ typedef enum pc_option {
     PC_OPT_KERNEL_TIMERS = 5,   /* 1: direct launches bracketed by CUDA events on the handle's
                                    stream, per-class times in pc_stats (measurement mode;
                                    implies one sample chain)                                */
-    PC_OPT_SAMPLE_CHAINS = 6    /* 1..8 (default 4): independent sample chains in flight.  Chain c
+    PC_OPT_SAMPLE_CHAINS = 6,   /* 1..8 (default 4): independent sample chains in flight.  Chain c
                                    traces samples c, c+n, ... with its own ray/path/hit state on its
                                    own stream so the launches of different samples overlap; chains
                                    > 0 accumulate separately and are added in chain order at the
                                    end of pc_trace (deterministic; differs from 1 chain only in
                                    float summation order)                                   */
+    PC_OPT_FUSE_TRACE = 7       /* 1: a bounce's occlusion test (+ emissive accumulation) and the
+                                   next bounce's closest-hit query run as ONE persistent launch;
+                                   results are bit-identical to 0 (two launches)              */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */

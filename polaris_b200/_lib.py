@@ -65,9 +65,9 @@ assert ctypes.sizeof(BlockRequest) == 48
 BUF_RAYS0, BUF_RAYS1, BUF_RAYS2, BUF_PATHS, BUF_HIT_FLAGS, BUF_INTERSECTIONS = 0, 1, 2, 3, 4, 5
 BUF_EMISSIVE_SAMPLES, BUF_TRACE_ACCUMULATOR, BUF_FRAME_ACCUMULATOR, BUF_FRAME_BUFFER, BUF_RAY_COUNTERS = 6, 7, 8, 9, 10
 # pc_option
-OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS = 0, 1, 2, 3, 4, 5, 6
-K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY = 0, 1, 2, 3, 4
-KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query"]
+OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE = 0, 1, 2, 3, 4, 5, 6, 7
+K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY, K_TRACE = 0, 1, 2, 3, 4, 5
+KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query", "k_trace"]
 # pc_status
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_ALLOC, ERR_COPY_TO_DEVICE, ERR_COPY_TO_HOST, ERR_KERNEL = 1, 2, 3, 4, 5, 6

@@ -20,6 +20,10 @@
 
 #include "../../include/polaris_cuda.h"
 #include "pc_kernels.cuh"
+
+#ifndef PC_DEFAULT_FUSE_TRACE
+#define PC_DEFAULT_FUSE_TRACE 1
+#endif
 #include "pc_layout.hpp"
 
 using namespace pc;
@@ -50,12 +54,12 @@ struct DevBuf {
 // boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
     uint32_t nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0;
     uint64_t sceneEpoch = 0;
     const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
         return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
-               fixq4 == o.fixq4 && chains == o.chains && sceneEpoch == o.sceneEpoch && seedsPtr == o.seedsPtr;
+               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sceneEpoch == o.sceneEpoch && seedsPtr == o.seedsPtr;
     }
 };
 
@@ -99,7 +103,7 @@ struct pc_tracer {
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE;
     int occGrid = 0;
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
@@ -224,10 +228,20 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         // ShadePrimaryRayMisses / ShadeIndirectRayMisses + ShadeHits (pipeline.go:134-146)
         {
             LaunchTimer lt(tr, PC_K_SHADE);
-            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
+            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
                                                             perSample, bounce, req.min_bounces_for_rr, a, tr->optFixQ4);
         }
         L++;
+        if (tr->optFuse && !tr->optRefOrder && bounce + 1 < nb) {
+            // RayIntersectionTest(2) + AccumulateEmissiveSamples(2) and the next bounce's RayIntersectionQuery
+            // (pipeline.go:160-165, :203-209) are independent: one persistent launch covers both
+            a = 1 - a;
+            LaunchTimer lt(tr, PC_K_TRACE);
+            k_trace<COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot);
+            L++;
+            slot += 2;
+            continue;
+        }
         // RayIntersectionTest(2) + AccumulateEmissiveSamples(2) (pipeline.go:160-165)
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
@@ -416,7 +430,18 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     if (occPerSM > 16) occPerSM = 16;
     tr->occGrid = tr->prop.multiProcessorCount * occPerSM;
     int shadePerSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, 0);
+    // the shade tile's staging area exceeds the 48 KB static limit: opt in to the dynamic size for both instances
+    cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
+    cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
+    {   // ask for just enough shared memory for SHADE_MIN_BLOCKS resident tiles; the rest of the 256 KB stays L1
+        const size_t want = (size_t)SHADE_MIN_BLOCKS * (sizeof(ShadeShared) + 1024);
+        int pct = (int)((want * 100 + tr->prop.sharedMemPerMultiprocessor - 1) / tr->prop.sharedMemPerMultiprocessor);
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, sizeof(ShadeShared));
+    if (shadePerSM > SHADE_MIN_BLOCKS) shadePerSM = SHADE_MIN_BLOCKS;
     if (shadePerSM < 1) shadePerSM = 1;
     tr->shadeGrid = tr->prop.multiProcessorCount * shadePerSM;
     tr->sc.sceneDiffuseMat = -1;
@@ -473,6 +498,7 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_USE_GRAPH: tr->optGraph = value != 0; break;
         case PC_OPT_FIX_Q4: tr->optFixQ4 = value != 0; break;
         case PC_OPT_KERNEL_TIMERS: tr->optTimers = value != 0; break;
+        case PC_OPT_FUSE_TRACE: tr->optFuse = value != 0; break;
         case PC_OPT_SAMPLE_CHAINS:
             if (value < 1 || value > MAX_CHAINS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample chains must be in [1, %d]", MAX_CHAINS);
             tr->optChains = value;
@@ -644,7 +670,7 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.chains = nc; key.sceneEpoch = tr->sceneEpoch; key.seedsPtr = tr->seedsDev.p;
+            key.chains = nc; key.fuse = tr->optFuse; key.sceneEpoch = tr->sceneEpoch; key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;

@@ -8,7 +8,8 @@
 //                   warp-packet traversal (shared stack + votes, the Guenther et al. scheme the
 //                   reference uses on GPUs, intersect.cl:353-575) or per-ray traversal
 //   k_shade         shadePrimaryRayMisses / shadeIndirectRayMisses + shadeHits
-//                   (pt_integrator.cl:17-275): 256-ray CTA tiles sorted by material, then STABLE
+//                   (pt_integrator.cl:17-275): 1024-ray CTA tiles sorted by material, shaded in 32-ray
+//                   chunks that the CTA's warps pull from a shared counter, then STABLE
 //                   compaction of the occlusion and indirect rays (ballot + popc per warp, offsets
 //                   across the CTA, a single-pass decoupled look-back across tiles, ticket ordered),
 //                   so ray order == parent ray order, which is what makes bounce >= 1 reproducible
@@ -16,6 +17,7 @@
 //   k_occlusion     rayIntersectionTest + accumulateEmissiveSamples (intersect.cl:26-180,
 //                   pt_integrator.cl:278-296)
 //   k_query         rayIntersectionQuery (intersect.cl:184-347) for the indirect rays
+//   k_trace         k_occlusion of bounce b + k_query of bounce b+1 in one persistent launch (default)
 //   k_clear / k_merge / k_tonemap   accumulator.cl:5-19, hdr.cl:5-28
 //
 // The traversal kernels are persistent: the grid is a fixed multiple of the SM count and every
@@ -34,7 +36,7 @@ constexpr int TRAV_BLOCK = 128;   // 4 warps
 #endif
 constexpr int SHADE_BLOCK = PC_SHADE_BLOCK;
 #ifndef SHADE_MIN_BLOCKS
-#define SHADE_MIN_BLOCKS 3
+#define SHADE_MIN_BLOCKS 2   // 2 x 256 threads x 128 registers: no spills in shadeHit (3 blocks = 80 registers spilled 280 B)
 #endif
 #ifndef PC_TRAV_MIN_BLOCKS
 #define PC_TRAV_MIN_BLOCKS 8
@@ -566,6 +568,64 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
     }
 }
 
+// k_trace: the bounce's two independent traversal stages in ONE persistent launch -- the closest-hit
+// query of the indirect rays (rays[a]) and the any-hit test of the occlusion rays (rays[2]) with its
+// emissive accumulation.  Neither reads what the other writes (hits / hit flags vs. the trace
+// accumulator), the reference only runs them back to back because its host loop is serial
+// (pipeline.go:160-165 then :203-209).  One queue covers both: the first ceil32(nQuery) items are
+// query units (the longer walks first, so the launch's tail is made of the cheap any-hit rays),
+// the rest occlusion units.  Saves one launch tail per bounce.
+template <bool COUNT>
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot) {
+    const uint32_t nQ = (uint32_t)ctl->numRays[a], nO = (uint32_t)ctl->numRays[2];
+    const uint32_t unitsQ = (nQ + 31u) & ~31u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)nQ);
+        atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
+    }
+    TravStats st{0, 0, 0};
+    uint32_t missed = 0, unocc = 0;
+    uint32_t *head = &ctl->queueHead[queueSlot];
+    const Ray *qrays = fb.rays[a], *orays = fb.rays[2];
+    for (;;) {
+        const uint32_t unit = next_unit(head);
+        if (unit >= unitsQ + nO) break;
+        if (unit < unitsQ) {
+            const uint32_t i = unit + lane_id();
+            if (i < nQ) {
+                const Ray r = ld_ray(qrays + i);
+                Hit best;
+                const int hit = traverse<false, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+                __stcs(fb.hitFlags + i, (uint32_t)hit);
+                st_hit(fb.hits + i, best.wuvt, best.inst, best.tri);
+                if (COUNT && !hit) missed++;
+            }
+        } else {
+            const uint32_t i = unit - unitsQ + lane_id();
+            if (i < nO) {
+                const Ray r = ld_ray(orays + i);
+                Hit best;
+                const int hit = traverse<true, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+                if (!hit) {
+                    const uint32_t pixel = fb.paths[(uint32_t)r.dir.w].meta.x;  // rayGetPathIndex (util/ray.cl:26-28)
+                    const float4 s = __ldcs(fb.emissiveSamples + i);
+                    float4 c = fb.traceAcc[pixel];
+                    c.x += s.x; c.y += s.y; c.z += s.z;
+                    fb.traceAcc[pixel] = c;
+                    if (COUNT) unocc++;
+                }
+            }
+        }
+    }
+    if (COUNT) {
+        warp_add_stat(ctl, ST_NODES, st.nodes);
+        warp_add_stat(ctl, ST_TRIS, st.tris);
+        warp_add_stat(ctl, ST_INSTANCES, st.instances);
+        warp_add_stat(ctl, ST_MISSED, missed);
+        warp_add_stat(ctl, ST_UNOCCLUDED, unocc);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Decoupled look-back over the shade TILES' (occlusion, indirect) totals.  A tile is the 32 rays a
 // warp shades at once; tiles are handed out by ticket, so tile t covers rays [32t, 32t+32) and every
@@ -612,47 +672,65 @@ __device__ __forceinline__ void lookback(volatile unsigned long long *status, ui
 
 // ------------------------------------------------------------------------------------------------
 // k_shade: shadePrimaryRayMisses / shadeIndirectRayMisses / shadeHits for rays[a][0 .. numRays[a]),
-// persistent over CTA tiles of SHADE_BLOCK consecutive rays handed out by ticket.
+// persistent over CTA tiles of SHADE_TILE consecutive rays handed out by ticket.
 //
 // A warp that simply shades 32 consecutive rays meets up to six different materials (plus misses) and
 // executes every BxDF / light / texture path present one after the other: measured on config 2 (ncu,
 // profiles/) 13 of 32 lanes were active and 26 % of the stalls were instruction fetch (100 KB of shading
 // code wanted by all warps all the time).  Sorting the tile by material first executes 38 % fewer warp
-// instructions; 256-ray tiles beat 128 (purer warps) and 512 (too few resident CTAs).
-//   1. each thread reads the (hit flag, triangle) of its ray and takes the triangle's material root
-//      as sort key; a counting sort over the CTA (warp match + a 256-entry histogram scan in shared
-//      memory) yields a permutation that groups equal materials;
-//   2. thread t shades ray perm[t]: warps now hold (mostly) one material each;
+// instructions.
+//   1. each thread reads the (hit flag, triangle) of its SHADE_RPT rays and takes the triangle's material
+//      root as sort key; a counting sort over the CTA (warp match + shared atomics for the per-key counts,
+//      a 64-entry scan) yields a permutation that groups equal materials;
+//   2. the warps pull 32-ray chunks of the sorted tile from a shared counter and shade them: a chunk holds
+//      (mostly) one material, and a warp with a cheap chunk takes the next one instead of idling;
 //   3. results are staged in shared memory at the ray's ORIGINAL slot, compacted in original order
-//      (ballot + popc per warp, offsets across the CTA, ONE decoupled look-back per CTA tile) and
+//      (ballot + popc per 32-slot group, offsets across the tile, ONE decoupled look-back per tile) and
 //      written out -- the output order is parent ray order, whichever lane did the arithmetic for a ray.
 // ------------------------------------------------------------------------------------------------
 constexpr int SHADE_WARPS = SHADE_BLOCK / 32;
 constexpr int SHADE_KEYS = 64;  // histogram bins: material roots modulo 62, misses, inactive lanes
 constexpr uint32_t KEY_MISS = SHADE_KEYS - 2, KEY_INACTIVE = SHADE_KEYS - 1;
+// Rays per thread and tile.  A tile is SHADE_BLOCK * SHADE_RPT consecutive rays; after the sort the CTA's
+// warps PULL 32-ray chunks of the sorted tile from a shared counter, so a warp that drew a cheap material
+// (diffuse) takes the next chunk instead of waiting at the tile's barrier for the warp that drew the
+// rough dielectric: with one chunk per warp (the r01c kernel) ncu showed 52 % of the warp stalls at
+// barriers.  SHADE_RPT * SHADE_WARPS <= 32 (one warp scans the per-group counts).
+// MEASURED (B200, config 2 at 128 spp, profiles/ab_r01de.txt), Mrays/s for (threads, rays per thread, CTAs per SM):
+// (256,1,3) 3216 = the r01c kernel | (256,2,3) 3571 | (256,3,3) 3547 | (256,4,2 @80 regs) 3428 | (256,2,2) 3546 |
+// (256,3,2) 3679 | (256,4,2) 3833 <- default | (512,2,1) 3705 | (128,4,4) 3497 | (128,4,5) 3268 | (128,8,3) 3224.
+// ncu on the default: 28.3 of 32 lanes active (21.3 before), barrier stalls 26 % (52 %), IPC 1.00 (0.75).
+#ifndef PC_SHADE_RPT
+#define PC_SHADE_RPT 4
+#endif
+constexpr int SHADE_RPT = PC_SHADE_RPT;
+constexpr int SHADE_TILE = SHADE_BLOCK * SHADE_RPT;
+constexpr int SHADE_GROUPS = SHADE_TILE / 32;
+static_assert(SHADE_GROUPS <= 32, "one warp scans the per-group counts");
 
 struct ShadeShared {
-    float occ[10][SHADE_BLOCK];   // origin.xyz, maxDist, dir.xyz, sample.xyz   (struct of arrays: conflict free)
-    float ind[6][SHADE_BLOCK];    // origin.xyz, dir.xyz
-    float pathIndexF[SHADE_BLOCK];
-    uint32_t hitTri[SHADE_BLOCK];  // triangle of the hit, 0xFFFFFFFF for a miss
-    uint32_t hist[SHADE_KEYS * SHADE_WARPS];
-    uint16_t perm[SHADE_BLOCK];
-    uint8_t flags[SHADE_BLOCK];    // bit 0 occlusion ray wanted, bit 1 indirect ray wanted
-    uint32_t warpOcc[SHADE_WARPS], warpInd[SHADE_WARPS];
-    uint32_t tile, occBase, indBase;
+    float occ[10][SHADE_TILE];   // origin.xyz, maxDist, dir.xyz, sample.xyz   (struct of arrays: conflict free)
+    float ind[6][SHADE_TILE];    // origin.xyz, dir.xyz
+    float pathIndexF[SHADE_TILE];
+    uint32_t hitTri[SHADE_TILE];  // triangle of the hit, 0xFFFFFFFF for a miss
+    uint16_t perm[SHADE_TILE];
+    uint8_t flags[SHADE_TILE];    // bit 0 occlusion ray wanted, bit 1 indirect ray wanted
+    uint32_t hist[SHADE_KEYS];    // per-key counts, then the keys' first positions in perm
+    uint32_t groupOcc[SHADE_GROUPS], groupInd[SHADE_GROUPS];  // per 32-slot group: counts, then exclusive offsets
+    uint32_t tile, occBase, indBase, nextChunk, activeChunks;
 };
 
 template <bool COUNT>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                       unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
                                                       uint32_t minBouncesForRR, int a, int fixQ4) {
-    __shared__ ShadeShared sh;
+    extern __shared__ __align__(16) unsigned char shade_smem[];
+    ShadeShared &sh = *reinterpret_cast<ShadeShared *>(shade_smem);
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t n = (uint32_t)ctl->numRays[a];
-    const uint32_t nTiles = (n + SHADE_BLOCK - 1u) / SHADE_BLOCK;
+    const uint32_t nTiles = (n + SHADE_TILE - 1u) / SHADE_TILE;
     if (n == 0 && blockIdx.x == 0 && tid == 0) {  // resources.go:230-238: both counters reset
         ctl->numRays[2] = 0;
         ctl->numRays[1 - a] = 0;
@@ -661,56 +739,68 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
     uint32_t shaded = 0;
     for (;;) {
         __syncthreads();  // the previous tile's shared state is no longer in use
-        if (tid == 0) sh.tile = atomicAdd(&ctl->ticket[bounce], 1u);
-        for (int k = tid; k < SHADE_KEYS * SHADE_WARPS; k += SHADE_BLOCK) sh.hist[k] = 0u;
+        if (tid == 0) { sh.tile = atomicAdd(&ctl->ticket[bounce], 1u); sh.nextChunk = 0u; }
+        if (tid < SHADE_KEYS) sh.hist[tid] = 0u;
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= nTiles) break;
-        const uint32_t base = tile * SHADE_BLOCK;
-        // ---- 1. sort key of my own ray
-        uint32_t key = KEY_INACTIVE;
-        {
-            const uint32_t i = base + tid;
-            uint32_t tri = 0xFFFFFFFFu;
+        const uint32_t base = tile * SHADE_TILE;
+        // ---- 1. sort keys of my SHADE_RPT rays (slot = r * SHADE_BLOCK + tid: coalesced), counted per key.
+        //         Which thread later shades which ray does not matter (results are staged at the ray's slot),
+        //         so the position inside a key's range is simply the order of arrival.
+        uint32_t key[SHADE_RPT], rank[SHADE_RPT];
+#pragma unroll
+        for (int r = 0; r < SHADE_RPT; r++) {
+            const uint32_t slot = r * SHADE_BLOCK + tid, i = base + slot;
+            uint32_t k = KEY_INACTIVE, tri = 0xFFFFFFFFu;
             if (i < n) {
-                key = KEY_MISS;
+                k = KEY_MISS;
                 if (__ldcs(fb.hitFlags + i)) {
                     tri = __ldcs(&fb.hits[i].meta).y;
-                    key = PC_LDG(sc.matIndex + tri) % (uint32_t)(SHADE_KEYS - 2);
+                    k = PC_LDG(sc.matIndex + tri) % (uint32_t)(SHADE_KEYS - 2);
                 }
             }
-            sh.hitTri[tid] = tri;
+            sh.hitTri[slot] = tri;
+            sh.flags[slot] = 0;
+            const unsigned peers = __match_any_sync(FULL, k);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t first = 0;
+            if ((int)lane == leader) first = atomicAdd(&sh.hist[k], (uint32_t)__popc(peers));
+            first = __shfl_sync(FULL, first, leader);
+            key[r] = k;
+            rank[r] = first + (uint32_t)__popc(peers & ltMask);
         }
-        const unsigned peers = __match_any_sync(FULL, key);
-        if (lane == (unsigned)(__ffs((int)peers) - 1)) sh.hist[key * SHADE_WARPS + warp] = (uint32_t)__popc(peers);
         __syncthreads();
-        if (warp == 0) {  // exclusive scan of the (key major, warp minor) histogram: 8 entries per lane
-            constexpr int PER = SHADE_KEYS * SHADE_WARPS / 32;
-            uint32_t v[PER], sum = 0;
-#pragma unroll
-            for (int k = 0; k < PER; k++) { v[k] = sh.hist[lane * PER + k]; sum += v[k]; }
+        if (warp == 0) {  // exclusive scan of the 64 key counts: 2 per lane
+            const uint32_t v0 = sh.hist[2 * lane], v1 = sh.hist[2 * lane + 1], sum = v0 + v1;
             uint32_t incl = sum;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, incl, d);
+                const uint32_t o = __shfl_up_sync(FULL, incl, d);
                 if ((int)lane >= d) incl += o;
             }
-            uint32_t run = incl - sum;
-#pragma unroll
-            for (int k = 0; k < PER; k++) { sh.hist[lane * PER + k] = run; run += v[k]; }
+            const uint32_t run = incl - sum;
+            sh.hist[2 * lane] = run;
+            sh.hist[2 * lane + 1] = run + v0;
+            if (lane == 31) sh.activeChunks = (run + v0 + 31u) / 32u;  // KEY_INACTIVE sorts last and is never shaded
         }
         __syncthreads();
-        sh.perm[sh.hist[key * SHADE_WARPS + warp] + (uint32_t)__popc(peers & ltMask)] = (uint16_t)tid;
+#pragma unroll
+        for (int r = 0; r < SHADE_RPT; r++) sh.perm[sh.hist[key[r]] + rank[r]] = (uint16_t)(r * SHADE_BLOCK + tid);
         __syncthreads();
-        // ---- 2. shade ray perm[tid]
-        const uint32_t slot = sh.perm[tid];
-        const uint32_t i = base + slot;
-        ShadeOut so;
-        so.wantOcc = false; so.wantInd = false;
-        float pathIndexF = 0.0f;
-        if (i < n) {
+        // ---- 2. warps pull 32-ray chunks of the sorted tile
+        const uint32_t activeChunks = sh.activeChunks;
+        for (;;) {
+            uint32_t c = 0;
+            if (lane == 0) c = atomicAdd(&sh.nextChunk, 1u);
+            c = __shfl_sync(FULL, c, 0);
+            if (c >= activeChunks) break;
+            const uint32_t slot = sh.perm[c * 32u + lane];
+            const uint32_t i = base + slot;
+            if (i >= n) continue;
+            ShadeOut so;
+            so.wantOcc = false; so.wantInd = false;
             const float4 rd = __ldcs(&fb.rays[a][i].dir);
-            pathIndexF = rd.w;
             const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
             const uint32_t tri = sh.hitTri[slot];
             if (tri == 0xFFFFFFFFu) {
@@ -718,52 +808,61 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                     float3 kd = shadeMiss(sc, xyz(rd));
                     PathRec p = ld_path(fb.paths + pathIndex);
                     float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
-                    float4 c = fb.traceAcc[p.meta.x];
-                    c.x += add.x; c.y += add.y; c.z += add.z;
-                    fb.traceAcc[p.meta.x] = c;
+                    float4 cc = fb.traceAcc[p.meta.x];
+                    cc.x += add.x; cc.y += add.y; cc.z += add.z;
+                    fb.traceAcc[p.meta.x] = cc;
                 }
-            } else {
-                shaded++;
-                const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
-                const PathRec p = ld_path(fb.paths + pathIndex);
-                shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, i, bounce, minBouncesForRR, randSeed, so);
-                if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
-                if (so.accum) {
-                    const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
-                    float4 c = fb.traceAcc[dst];
-                    c.x += so.accumAdd.x; c.y += so.accumAdd.y; c.z += so.accumAdd.z;
-                    fb.traceAcc[dst] = c;
-                }
-                if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
+                continue;
+            }
+            shaded++;
+            const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
+            const PathRec p = ld_path(fb.paths + pathIndex);
+            shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, i, bounce, minBouncesForRR, randSeed, so);
+            if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
+            if (so.accum) {
+                const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
+                float4 cc = fb.traceAcc[dst];
+                cc.x += so.accumAdd.x; cc.y += so.accumAdd.y; cc.z += so.accumAdd.z;
+                fb.traceAcc[dst] = cc;
+            }
+            if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
+            // ---- 3. stage at the ORIGINAL slot
+            sh.flags[slot] = (uint8_t)((so.wantOcc ? 1u : 0u) | (so.wantInd ? 2u : 0u));
+            sh.pathIndexF[slot] = rd.w;
+            if (so.wantOcc) {
+                sh.occ[0][slot] = so.occOrigin.x; sh.occ[1][slot] = so.occOrigin.y; sh.occ[2][slot] = so.occOrigin.z;
+                sh.occ[3][slot] = so.occMaxDist;
+                sh.occ[4][slot] = so.occDir.x; sh.occ[5][slot] = so.occDir.y; sh.occ[6][slot] = so.occDir.z;
+                sh.occ[7][slot] = so.occSample.x; sh.occ[8][slot] = so.occSample.y; sh.occ[9][slot] = so.occSample.z;
+            }
+            if (so.wantInd) {
+                sh.ind[0][slot] = so.indOrigin.x; sh.ind[1][slot] = so.indOrigin.y; sh.ind[2][slot] = so.indOrigin.z;
+                sh.ind[3][slot] = so.indDir.x; sh.ind[4][slot] = so.indDir.y; sh.ind[5][slot] = so.indDir.z;
             }
         }
-        // ---- 3. stage at the ORIGINAL slot
-        sh.flags[slot] = (uint8_t)((so.wantOcc ? 1u : 0u) | (so.wantInd ? 2u : 0u));
-        sh.pathIndexF[slot] = pathIndexF;
-        if (so.wantOcc) {
-            sh.occ[0][slot] = so.occOrigin.x; sh.occ[1][slot] = so.occOrigin.y; sh.occ[2][slot] = so.occOrigin.z;
-            sh.occ[3][slot] = so.occMaxDist;
-            sh.occ[4][slot] = so.occDir.x; sh.occ[5][slot] = so.occDir.y; sh.occ[6][slot] = so.occDir.z;
-            sh.occ[7][slot] = so.occSample.x; sh.occ[8][slot] = so.occSample.y; sh.occ[9][slot] = so.occSample.z;
-        }
-        if (so.wantInd) {
-            sh.ind[0][slot] = so.indOrigin.x; sh.ind[1][slot] = so.indOrigin.y; sh.ind[2][slot] = so.indOrigin.z;
-            sh.ind[3][slot] = so.indDir.x; sh.ind[4][slot] = so.indDir.y; sh.ind[5][slot] = so.indDir.z;
-        }
         __syncthreads();
-        // ---- 4. stable compaction in original order (replaces pt_integrator.cl:162,176,188-197)
-        const uint32_t f = sh.flags[tid];
-        const unsigned occMask = __ballot_sync(FULL, (f & 1u) != 0u), indMask = __ballot_sync(FULL, (f & 2u) != 0u);
-        if (lane == 0) { sh.warpOcc[warp] = (uint32_t)__popc(occMask); sh.warpInd[warp] = (uint32_t)__popc(indMask); }
-        __syncthreads();
-        uint32_t occOff = 0, indOff = 0, occTot = 0, indTot = 0;
+        // ---- 4. stable compaction in original order (replaces pt_integrator.cl:162,176,188-197): warp w owns the
+        //         32-slot groups w, w + SHADE_WARPS, ...
+        unsigned occMask[SHADE_RPT], indMask[SHADE_RPT];
 #pragma unroll
-        for (int wv = 0; wv < SHADE_WARPS; wv++) {
-            const uint32_t o = sh.warpOcc[wv], q = sh.warpInd[wv];
-            if (wv < (int)warp) { occOff += o; indOff += q; }
-            occTot += o; indTot += q;
+        for (int r = 0; r < SHADE_RPT; r++) {
+            const uint32_t g = r * SHADE_WARPS + warp;
+            const uint32_t f = sh.flags[g * 32u + lane];
+            occMask[r] = __ballot_sync(FULL, (f & 1u) != 0u);
+            indMask[r] = __ballot_sync(FULL, (f & 2u) != 0u);
+            if (lane == 0) { sh.groupOcc[g] = (uint32_t)__popc(occMask[r]); sh.groupInd[g] = (uint32_t)__popc(indMask[r]); }
         }
+        __syncthreads();
         if (warp == 0) {
+            const uint32_t o = lane < SHADE_GROUPS ? sh.groupOcc[lane] : 0u, q = lane < SHADE_GROUPS ? sh.groupInd[lane] : 0u;
+            uint32_t io = o, iq = q;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t uo = __shfl_up_sync(FULL, io, d), uq = __shfl_up_sync(FULL, iq, d);
+                if ((int)lane >= d) { io += uo; iq += uq; }
+            }
+            if (lane < SHADE_GROUPS) { sh.groupOcc[lane] = io - o; sh.groupInd[lane] = iq - q; }
+            const uint32_t occTot = __shfl_sync(FULL, io, 31), indTot = __shfl_sync(FULL, iq, 31);
             uint32_t occBase, indBase;
             lookback(status, tile, occTot, indTot, occBase, indBase);
             if (lane == 0) {
@@ -779,17 +878,21 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             }
         }
         __syncthreads();
-        const float pif = sh.pathIndexF[tid];
-        if (f & 1u) {  // pt_integrator.cl:200-204
-            const uint32_t k = sh.occBase + occOff + (uint32_t)__popc(occMask & ltMask);
-            __stcs(fb.emissiveSamples + k, make_float4(sh.occ[7][tid], sh.occ[8][tid], sh.occ[9][tid], 0.0f));
-            st_ray(fb.rays[2] + k, make_float4(sh.occ[0][tid], sh.occ[1][tid], sh.occ[2][tid], sh.occ[3][tid]),
-                   make_float4(sh.occ[4][tid], sh.occ[5][tid], sh.occ[6][tid], pif));
-        }
-        if (f & 2u) {  // :207-210
-            const uint32_t k = sh.indBase + indOff + (uint32_t)__popc(indMask & ltMask);
-            st_ray(fb.rays[1 - a] + k, make_float4(sh.ind[0][tid], sh.ind[1][tid], sh.ind[2][tid], FLT_MAX),
-                   make_float4(sh.ind[3][tid], sh.ind[4][tid], sh.ind[5][tid], pif));
+#pragma unroll
+        for (int r = 0; r < SHADE_RPT; r++) {
+            const uint32_t g = r * SHADE_WARPS + warp, slot = g * 32u + lane;
+            const float pif = sh.pathIndexF[slot];
+            if (occMask[r] & (1u << lane)) {  // pt_integrator.cl:200-204
+                const uint32_t k = sh.occBase + sh.groupOcc[g] + (uint32_t)__popc(occMask[r] & ltMask);
+                __stcs(fb.emissiveSamples + k, make_float4(sh.occ[7][slot], sh.occ[8][slot], sh.occ[9][slot], 0.0f));
+                st_ray(fb.rays[2] + k, make_float4(sh.occ[0][slot], sh.occ[1][slot], sh.occ[2][slot], sh.occ[3][slot]),
+                       make_float4(sh.occ[4][slot], sh.occ[5][slot], sh.occ[6][slot], pif));
+            }
+            if (indMask[r] & (1u << lane)) {  // :207-210
+                const uint32_t k = sh.indBase + sh.groupInd[g] + (uint32_t)__popc(indMask[r] & ltMask);
+                st_ray(fb.rays[1 - a] + k, make_float4(sh.ind[0][slot], sh.ind[1][slot], sh.ind[2][slot], FLT_MAX),
+                       make_float4(sh.ind[3][slot], sh.ind[4][slot], sh.ind[5][slot], pif));
+            }
         }
     }
     if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);

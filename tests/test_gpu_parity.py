@@ -139,7 +139,7 @@ def test_bounce0_radiance(key, w, h, seed_cfg):
 def test_full_depth_single_sample(key, w, h):
     sc = C.small_scene(key, w, h)
     seeds = T.splitmix_seeds(4, 6)
-    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h, counters=1)
+    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h, counters=1, fuse_trace=0)
     ro, rg = T.make_block_request(w, h, spp=1), T.make_block_request(w, h, spp=1)
     orc.trace(ro, seeds)
     cu.trace(rg, seeds)
@@ -147,18 +147,19 @@ def test_full_depth_single_sample(key, w, h):
     so, sg = orc.stats().device, cu.stats().device
     for k in ("query_rays", "occlusion_rays", "shaded_hits", "indirect_emitted", "occlusion_emitted", "unoccluded", "missed_query_rays"):
         assert abs(so[k] - sg[k]) <= max(4, int(1e-3 * so[k])), (k, so[k], sg[k])
-    assert sg["kernel_launches"] == 2 + (1 + 1 + 5 * 2 + 4)
+    assert sg["kernel_launches"] == 2 + (1 + 1 + 5 * 2 + 4)  # begin, primary, 5 x (shade, occlusion), 4 x query; fused: 4 launches fewer
     cu.close()
 
 
 def test_variants_bit_identical():
-    """packet vs per-ray primary traversal, graph replay vs direct launches, counters on/off and the
-    reference-order traversal all produce the same accumulator bits (GPU vs GPU)."""
+    """packet vs per-ray primary traversal, graph replay vs direct launches, counters on/off, the fused
+    occlusion + query launch and the reference-order traversal all produce the same accumulator bits (GPU vs GPU)."""
     w = h = 160
     sc = C.small_scene("c2", w, h)
     seeds = T.splitmix_seeds(5, 2 * 6)
     ref = None
-    for opts in ({}, {"primary_packets": 0}, {"use_graph": 0}, {"counters": 1}, {"reference_order": 1}):
+    for opts in ({}, {"primary_packets": 0}, {"use_graph": 0}, {"counters": 1}, {"reference_order": 1}, {"fuse_trace": 0},
+                 {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}):
         cu = C.cuda_for(sc, w, h, **opts)
         cu.trace(T.make_block_request(w, h, spp=2), seeds)
         acc = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
