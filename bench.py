@@ -167,6 +167,44 @@ def cpu_trace_sample(sc, w, h, spp, config_number, rows=None):
     return rays / dt / 1e6, cores, kind, dt, rays
 
 
+def opencl_reference_sample(sc, w, h, spp, config_number, rows=None):
+    """The reference's own OpenCL program + launch discipline on this box's OpenCL device (on the GPU box: the same
+    B200 through NVIDIA's OpenCL driver, oracle/cl_device.py), bounded sample of the same workload.  A reported
+    baseline next to `cpu_baseline`; returns a dict for the JSON line."""
+    try:
+        from oracle import cl_device
+        from polaris_b200 import tracer as T
+
+        if not cl_device.available():
+            return {"unavailable": "no OpenCL device or no embedded reference program (oracle/_ref) on this box"}
+        tr = cl_device.ClDeviceTracer()
+        tr.init()
+        tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
+        tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+        tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
+        bh = rows or h
+        seeds = T.splitmix_seeds(config_number, spp * (1 + NUM_BOUNCES))
+        best = None
+        for _ in range(2):  # first pass warms the driver's lazily built kernels
+            req = T.make_block_request(w, h, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+            t0 = time.perf_counter()
+            tr.trace(req, seeds)
+            tr.merge_output(tr, req)
+            tr.sync_framebuffer(T.make_block_request(w, h, spp=spp, exposure=EXPOSURE), want_pixels=False)
+            dt = time.perf_counter() - t0
+            d = tr.stats().device
+            rays = d["query_rays"] + d["occlusion_rays"]
+            if best is None or rays / dt > best[0]:
+                best = (rays / dt, dt, rays, d["kernel_launches"])
+        desc = tr.dev.describe()
+        tr.close()
+        return {"value": best[0] / 1e6, "unit": "Mrays/s", "kind": "reference OpenCL kernels + launch discipline (clFinish per launch), same GPU",
+                "device": desc["device"], "platform": desc["platform_version"], "launches": int(best[3]),
+                "sample": f"{w}x{bh} rows of the {w}x{h} frame, {spp} spp ({best[2]} rays in {best[1]:.3f}s, best of 2)"}
+    except Exception as e:  # a baseline must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
@@ -199,6 +237,9 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_opencl:
+        line["reference_on_gpu"] = opencl_reference_sample(sc, w, h, 8 if n == 1 else 2, cfgno, rows)
+        log(f"[bench:reference] reference OpenCL path on this box's GPU: {line['reference_on_gpu']}")
     emit(line)
     return 0
 
@@ -349,6 +390,11 @@ def run_cuda_single(args):
         cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind,
                "sample": f"{w}x{cpu_rows} rows of the {w}x{h} frame, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
         log(f"[bench] cpu baseline ({kind}, {cores} cores): {v:.2f} Mrays/s")
+    ocl = None
+    if not args.no_cpu and not args.no_opencl:
+        ocl_rows = h if w * h <= 1024 * 1024 else max(16, (2048 * 1024) // w)
+        ocl = opencl_reference_sample(sc, w, h, 8, cfgno, ocl_rows)
+        log(f"[bench] reference OpenCL path on this GPU: {ocl}")
 
     line = {
         "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
@@ -356,7 +402,7 @@ def run_cuda_single(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp, args.config, sc),
         "spp_mpix_per_s": w * h * spp * args.steps / dt / 1e6, "gpu_launches": int(tot_launch), "clocks": clk,
         "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ocl,
     }
     emit(line)
     return 0
@@ -519,6 +565,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per step (debugging only; invalidates the config)")
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-opencl", action="store_true", help="skip the reference-OpenCL-kernels-on-this-GPU baseline")
     ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
     ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")
     ap.add_argument("--opt", action="append", default=[], help="NAME=VALUE tracer option, e.g. PRIMARY_PACKETS=0 (experiments)")

@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import re
 import time
 
 import numpy as np
@@ -117,12 +118,9 @@ class _Api:
             lib.clGetExtensionFunctionAddress.argtypes = [ctypes.c_char_p]
             addr = lib.clGetExtensionFunctionAddress(b"clIcdGetPlatformIDsKHR")
             if addr:
-                icd = ctypes.CFUNCTYPE(i32, u32, P(vp), P(u32))(addr)
-        if icd is not None and not isinstance(icd, ctypes._CFuncPtr.__mro__[0]) or icd is not None:
-            try:
-                icd.restype, icd.argtypes = i32, [u32, P(vp), P(u32)]
-            except Exception:
-                pass
+                icd = ctypes.CFUNCTYPE(None)(addr)
+        if icd is not None:
+            icd.restype, icd.argtypes = i32, [u32, P(vp), P(u32)]
             rc = icd(8, plats, ctypes.byref(n))
             if rc == 0 and n.value > 0:
                 self.platform = vp(plats[0])
@@ -181,13 +179,23 @@ def available() -> bool:
         return False
 
 
-def program_source() -> bytes:
+# C++-style functional casts -- `uint(0)`, `int(x)`, `uchar(x)` -- appear at 14 places of the reference's program
+# (texture_sampler.cl:27-30,118-121,201-204, emissive_sampler.cl:236, debug.cl:46).  They are not OpenCL C: the
+# compiler the reference was developed against (Apple's) accepts them, NVIDIA's rejects them ("unexpected type
+# name 'uint': expected expression", profiles/cl_probe_r01.txt).  `T(x)` -> `(T)(x)` is the same conversion.
+_FUNCTIONAL_CAST = re.compile(rb"(?<![\w)])\b(uint|int|uchar)\(")
+
+
+def program_source(portable=True) -> bytes:
     lib = ref_binding.load()
     lib.pr_cl_program_source.restype = ctypes.c_void_p
     lib.pr_cl_program_source.argtypes = [P(u64)]
     n = u64(0)
     p = lib.pr_cl_program_source(ctypes.byref(n))
-    return ctypes.string_at(p, n.value)
+    src = ctypes.string_at(p, n.value)
+    if portable:
+        src = _FUNCTIONAL_CAST.sub(lambda m: b"(" + m.group(1) + b")(", src)
+    return src
 
 
 _KERNELS = ("clearAccumulator", "aggregateAccumulator", "generatePrimaryRays", "rayIntersectionTest", "rayIntersectionQuery",
@@ -276,7 +284,7 @@ class ClDevice:
         self.build_log = log.value.decode(errors="replace")
         self.build_seconds = time.perf_counter() - t0
         if rc != 0:
-            raise ClError(f"clBuildProgram: {rc}\n{self.build_log[-4000:]}")
+            raise ClError(f"clBuildProgram: {rc}\n{self.build_log[:6000]}")
         self.kernels = {}
         for k in _KERNELS:
             h = a.clCreateKernel(self.program, k.encode(), ctypes.byref(err))
