@@ -327,6 +327,96 @@ func (tr *Tracer) Trace(blockReq *tracer.BlockRequest) (time.Duration, error) {
 	return tr.stats.RenderTime, nil
 }
 
+// DebugFlag mirrors opencl.DebugFlag (tracer/opencl/pipeline.go:17-30) value for value.
+type DebugFlag uint16
+
+const (
+	NoDebug                     DebugFlag = 0
+	PrimaryRayIntersectionDepth DebugFlag = 1 << (iota + 0)
+	PrimaryRayIntersectionNormals
+	AllEmissiveSamples
+	VisibleEmissiveSamples
+	OccludedEmissiveSamples
+	Throughput
+	Accumulator
+	FrameBuffer
+)
+
+// DebugFrame is one dump of the debug buffer: what the reference writes to debug-<stage>[-<bounce>].png
+// (pipeline.go:113-200, dumpDebugBuffer :259-277).  Pix is FrameW*FrameH RGBA8, the layout image.RGBA wants.
+type DebugFrame struct {
+	Flag   DebugFlag
+	Bounce uint32
+	Pix    []byte
+}
+
+// FileName is the name opencl.MonteCarloIntegrator gives the dump.
+func (f DebugFrame) FileName() string {
+	switch f.Flag {
+	case PrimaryRayIntersectionDepth:
+		return "debug-primary-intersection-depth.png"
+	case PrimaryRayIntersectionNormals:
+		return "debug-primary-intersection-normals.png"
+	case AllEmissiveSamples:
+		return fmt.Sprintf("debug-emissive-all-%03d.png", f.Bounce)
+	case VisibleEmissiveSamples:
+		return fmt.Sprintf("debug-emissive-vis-%03d.png", f.Bounce)
+	case OccludedEmissiveSamples:
+		return fmt.Sprintf("debug-emissive-occ-%03d.png", f.Bounce)
+	case Throughput:
+		return fmt.Sprintf("debug-throughput-%03d.png", f.Bounce)
+	case Accumulator:
+		return fmt.Sprintf("debug-accumulator-%03d.png", f.Bounce)
+	}
+	return "debug.png"
+}
+
+// TraceDebug is Trace with the reference's debug stages switched on (MonteCarloIntegrator(debugFlags)): it returns
+// the debug-buffer dumps of the last sample in the order the reference writes its PNG files; the caller encodes them.
+func (tr *Tracer) TraceDebug(blockReq *tracer.BlockRequest, flags DebugFlag) ([]DebugFrame, time.Duration, error) {
+	tr.Lock()
+	defer tr.Unlock()
+	start := time.Now()
+	if _, err := tr.commitChanges(); err != nil {
+		return nil, time.Since(start), err
+	}
+	if !tr.hasScene {
+		return nil, time.Since(start), ErrNoSceneData
+	}
+	n := int(blockReq.SamplesPerPixel) * (1 + int(blockReq.NumBounces))
+	seeds := make([]uint32, n)
+	if tr.Seeds != nil {
+		seeds = tr.Seeds(n)
+	} else {
+		for i := range seeds {
+			seeds[i] = rand.Uint32()
+		}
+	}
+	count := int(C.pc_debug_frame_count(C.uint32_t(flags), C.uint32_t(blockReq.NumBounces)))
+	frameBytes := int(blockReq.FrameW) * int(blockReq.FrameH) * 4
+	pix := make([]byte, count*frameBytes+1)
+	infos := make([]C.pc_debug_frame, count+1)
+	req := toC(blockReq)
+	var st C.pc_stats
+	var got C.uint32_t
+	var sp *C.uint32_t
+	if n > 0 {
+		sp = (*C.uint32_t)(unsafe.Pointer(&seeds[0]))
+	}
+	rc := C.pc_trace_debug(tr.handle, &req, sp, C.size_t(n), C.uint32_t(flags), (*C.uint8_t)(unsafe.Pointer(&pix[0])),
+		C.uint64_t(count*frameBytes), &infos[0], C.uint32_t(count), &got, &st)
+	if rc != 0 {
+		return nil, time.Since(start), tr.lastError(rc)
+	}
+	blockReq.Seed = uint32(req.seed)
+	blockReq.AccumulatedSamples = uint32(req.accumulated_samples)
+	frames := make([]DebugFrame, int(got))
+	for i := range frames {
+		frames[i] = DebugFrame{Flag: DebugFlag(infos[i].flag), Bounce: uint32(infos[i].bounce), Pix: pix[i*frameBytes : (i+1)*frameBytes]}
+	}
+	return frames, time.Since(start), nil
+}
+
 // MergeOutput: tracer/opencl/tracer.go:279-286.  Called concurrently on the primary by every worker
 // goroutine (renderer/default.go:191); the library serialises per destination and returns without
 // waiting for the add, SyncFramebuffer is the fence.

@@ -205,6 +205,27 @@ int pc_trace_rows(pc_tracer *tr, const pc_block_request *req, void **device_ptr,
  * (what SaveFrameBuffer / CopyFrameBufferToOpenGLTexture read, pipeline.go:216-256). */
 int pc_sync_framebuffer(pc_tracer *tr, const pc_block_request *req, uint8_t *rgba_out);
 
+/* ---- debug pipeline stages: MonteCarloIntegrator(debugFlags) (pipeline.go:17-30,113-200) + kernels/debug.cl ----
+ * opencl.DebugFlag values (1 << iota, iota starting at 1).  PC_DEBUG_FRAMEBUFFER is the reference's
+ * SaveFrameBuffer post-process stage (pipeline.go:61-63,216-234): pass rgba_out to pc_sync_framebuffer. */
+typedef enum pc_debug_flag {
+    PC_DEBUG_PRIMARY_DEPTH = 2, PC_DEBUG_PRIMARY_NORMALS = 4, PC_DEBUG_ALL_EMISSIVE = 8, PC_DEBUG_VISIBLE_EMISSIVE = 16,
+    PC_DEBUG_OCCLUDED_EMISSIVE = 32, PC_DEBUG_THROUGHPUT = 64, PC_DEBUG_ACCUMULATOR = 128, PC_DEBUG_FRAMEBUFFER = 256
+} pc_debug_flag;
+typedef struct pc_debug_frame { uint32_t flag, bounce; } pc_debug_frame;
+/* Number of frames pc_trace_debug produces: depth + normals once, the other five once per bounce. */
+uint32_t pc_debug_frame_count(uint32_t debug_flags, uint32_t num_bounces);
+/* pc_trace with the debug stages switched on.  Every stage renders into the RGBA8 debug buffer
+ * (frame_w*frame_h*4 bytes, cleared first, resources.go:362-375) and the reference dumps it to
+ * debug-<stage>[-<bounce>].png, overwriting the file every sample: frames_out receives the dumps of the
+ * LAST sample back to back, in the order the reference writes them, infos[i] naming stage and bounce of
+ * frame i (the Go shim encodes the PNGs).  Direct launches, one sample chain, nothing fused: a debugging
+ * aid, not a fast path.  Like the reference's normals stage, matSelectNode runs on the real paths and may
+ * set their dispersion bits (debug.cl:94).  PC_ERR_INVALID_ARGUMENT when frames_out / infos are too small. */
+int pc_trace_debug(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds,
+                   uint32_t debug_flags, uint8_t *frames_out, uint64_t frames_cap_bytes,
+                   pc_debug_frame *infos, uint32_t infos_cap, uint32_t *n_frames, pc_stats *stats);
+
 /* ---- test / oracle hooks ---- */
 int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes);
 /* Upload n rays (32 B each) into rays0 and run one intersection kernel on them:

@@ -25,6 +25,7 @@ _SYMS = [
     ("po_upload_scene", ctypes.c_int, [vp, _P(SceneView)]),
     ("po_set_camera", ctypes.c_int, [vp, _P(f32), _P(f32)]),
     ("po_trace", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, _P(Stats)]),
+    ("po_trace_debug", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, u32, vp, u64, vp, u32, _P(u32), _P(Stats)]),
     ("po_merge_output", ctypes.c_int, [vp, vp, _P(BlockRequest)]),
     ("po_sync_framebuffer", ctypes.c_int, [vp, _P(BlockRequest), vp]),
     ("po_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),

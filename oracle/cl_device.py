@@ -200,7 +200,8 @@ def program_source(portable=True) -> bytes:
 
 _KERNELS = ("clearAccumulator", "aggregateAccumulator", "generatePrimaryRays", "rayIntersectionTest", "rayIntersectionQuery",
             "rayPacketIntersectionQuery", "shadeHits", "shadePrimaryRayMisses", "shadeIndirectRayMisses",
-            "accumulateEmissiveSamples", "tonemapSimpleReinhard")
+            "accumulateEmissiveSamples", "tonemapSimpleReinhard", "debugClearBuffer", "debugRayIntersectionDepth",
+            "debugRayIntersectionNormals", "debugEmissiveSamples", "debugThroughput", "debugAccumulator")
 
 
 class _Buf:
@@ -430,7 +431,7 @@ class ClDeviceTracer(Tracer):
         d = self.dev
         self.b = {"rays0": _Buf(d, px * 32), "rays1": _Buf(d, px * 32), "rays2": _Buf(d, px * 32), "paths": _Buf(d, px * 32),
                   "hitFlags": _Buf(d, px * 4), "intersections": _Buf(d, px * 32), "emissiveSamples": _Buf(d, px * 16),
-                  "traceAcc": _Buf(d, px * 16), "frameAcc": _Buf(d, px * 16), "frameBuffer": _Buf(d, px * 4),
+                  "traceAcc": _Buf(d, px * 16), "frameAcc": _Buf(d, px * 16), "frameBuffer": _Buf(d, px * 4), "debugOutput": _Buf(d, px * 4),
                   "cnt0": _Buf(d, 4), "cnt1": _Buf(d, 4), "cnt2": _Buf(d, 4)}
 
     def _upload_scene(self, sc):  # bufferSet.UploadSceneData (buffers.go:178-201)
@@ -469,7 +470,43 @@ class ClDeviceTracer(Tracer):
         d.set_args("rayIntersectionTest", [b[f"rays{buf}"], b[f"cnt{buf}"], s["bvhNodes"], s["meshInstances"], s["vertices"], b["hitFlags"]])
         d.exec("rayIntersectionTest", [num_pixels])
 
-    def trace(self, req, seeds=None):
+    # -- debug stages (resources.go:362-520, pipeline.go:113-200)
+    def _debug_stage(self, req, flag, bounce, a, frames):
+        d, b, s = self.dev, self.b, self.scene
+        px, n = self.w * self.h, int(req.frame_w) * int(req.block_h)
+        d.set_args("debugClearBuffer", [b["debugOutput"]])
+        d.exec("debugClearBuffer", [px])
+        if flag == _lib.DEBUG_PRIMARY_DEPTH:
+            t = b["intersections"].read(px * 32, _lib.INTERSECTION_DTYPE)["wuvt"][:, 3]  # ReadDataIntoSlice of the whole buffer
+            finite = t[t != np.finfo(np.float32).max]
+            max_depth = _f32(max(1.0, float(finite.max()))) if finite.size else _f32(1.0)
+            d.set_args("debugRayIntersectionDepth", [b[f"cnt{a}"], b["paths"], b["hitFlags"], b["intersections"], max_depth, b["debugOutput"]])
+            d.exec("debugRayIntersectionDepth", [n])
+        elif flag == _lib.DEBUG_PRIMARY_NORMALS:
+            d.set_args("debugRayIntersectionNormals", [b[f"rays{a}"], b[f"cnt{a}"], b["paths"], b["hitFlags"], b["intersections"], s["vertices"],
+                                                       s["normals"], s["uv"], s["materialIndices"], s["materialNodes"], s["textureMetadata"],
+                                                       s["textures"], b["debugOutput"]])
+            d.exec("debugRayIntersectionNormals", [n])
+        elif flag in (_lib.DEBUG_ALL_EMISSIVE, _lib.DEBUG_VISIBLE_EMISSIVE, _lib.DEBUG_OCCLUDED_EMISSIVE):
+            d.set_args("debugEmissiveSamples", [b["rays2"], b["cnt2"], b["paths"], b["hitFlags"], b["emissiveSamples"],
+                                                _u32(flag == _lib.DEBUG_VISIBLE_EMISSIVE), _u32(flag == _lib.DEBUG_OCCLUDED_EMISSIVE), b["debugOutput"]])
+            d.exec("debugEmissiveSamples", [n])
+        elif flag == _lib.DEBUG_THROUGHPUT:
+            d.set_args("debugThroughput", [b["paths"], b["debugOutput"]])
+            d.exec("debugThroughput", [n])
+        elif flag == _lib.DEBUG_ACCUMULATOR:
+            weight = _f32(1.0 / _f32(int(req.accumulated_samples) + int(req.samples_per_pixel)))
+            d.set_args("debugAccumulator", [weight, b["paths"], b["traceAcc"], b["debugOutput"]])
+            d.exec("debugAccumulator", [n])
+        if frames is not None:
+            frames.append((flag, bounce, b["debugOutput"].read(px * 4).reshape(self.h, self.w, 4)))
+
+    def trace_debug(self, req, seeds, debug_flags):
+        frames = []
+        self.trace(req, seeds, debug_flags=debug_flags, frames=frames)
+        return frames
+
+    def trace(self, req, seeds=None, debug_flags=0, frames=None):
         t0 = time.perf_counter()
         self._commit_changes()
         if not self._has_scene:
@@ -500,6 +537,10 @@ class ClDeviceTracer(Tracer):
             a = 0
             self._query(a, num_pixels, self._packets and num_pixels % 32 == 0)
             q_rays += num_pixels
+            keep = frames if sample + 1 == spp else None  # the reference overwrites its PNGs every sample
+            for f in (_lib.DEBUG_PRIMARY_DEPTH, _lib.DEBUG_PRIMARY_NORMALS):
+                if debug_flags & f:
+                    self._debug_stage(req, f, 0, a, keep)
             for bounce in range(nb):  # pipeline.go:132
                 if self.scene_diffuse != -1:
                     name = "shadePrimaryRayMisses" if bounce == 0 else "shadeIndirectRayMisses"
@@ -513,6 +554,8 @@ class ClDeviceTracer(Tracer):
                                          s["textureMetadata"], s["textures"], _u32(bounce), _u32(req.min_bounces_for_rr), _u32(ss[1 + bounce]),
                                          b["rays2"], b["cnt2"], b["emissiveSamples"], b[f"rays{1 - a}"], b[f"cnt{1 - a}"], b["traceAcc"]])
                 d.exec("shadeHits", [num_pixels])
+                if debug_flags & _lib.DEBUG_THROUGHPUT:
+                    self._debug_stage(req, _lib.DEBUG_THROUGHPUT, bounce, a, keep)
                 cnt = self._counters()  # not in the reference: only to report rays
                 occ_emitted += cnt[2]
                 ind_emitted += cnt[1 - a]
@@ -520,6 +563,9 @@ class ClDeviceTracer(Tracer):
                 o_rays += cnt[2]
                 d.set_args("accumulateEmissiveSamples", [b["rays2"], b["cnt2"], b["paths"], b["hitFlags"], b["emissiveSamples"], b["traceAcc"]])
                 d.exec("accumulateEmissiveSamples", [num_pixels])  # :165
+                for f in (_lib.DEBUG_ALL_EMISSIVE, _lib.DEBUG_VISIBLE_EMISSIVE, _lib.DEBUG_OCCLUDED_EMISSIVE, _lib.DEBUG_ACCUMULATOR):
+                    if debug_flags & f:
+                        self._debug_stage(req, f, bounce, a, keep)
                 if bounce + 1 < nb:  # :203-209
                     a = 1 - a
                     self._query(a, num_pixels)

@@ -913,7 +913,7 @@ struct Oracle {
     std::vector<uint32_t> hitFlags;
     std::vector<Intersection> intersections;
     std::vector<f4> emissiveSamples, traceAcc, frameAcc;
-    std::vector<uint8_t> frameBuffer;
+    std::vector<uint8_t> frameBuffer, debugOutput;
     int32_t numRays[3] = {0, 0, 0};
     int fixQ4 = 1;
     pc_stats stats{};
@@ -1148,6 +1148,150 @@ inline uint32_t nextSeed(uint64_t &s) {
     return (uint32_t)z;
 }
 
+// ------------------------------------------------------------------------------------------
+// kernels/debug.cl:16-156 + their launches (resources.go:362-520)
+// ------------------------------------------------------------------------------------------
+inline f3 debugToneMapAndGammaCorrect(f3 sample) {  // debug.cl:8-13 (DEBUG_TONEMAP_EXPOSURE 1.0f)
+    sample = sample * 1.0f;
+    f3 mapped = sample / (sample + 1.0f);
+    const float e = 1.0f / 2.2f;
+    return F3(cl_clamp(powf(mapped.x, e), 0.0f, 1.0f), cl_clamp(powf(mapped.y, e), 0.0f, 1.0f), cl_clamp(powf(mapped.z, e), 0.0f, 1.0f)) * 255.0f;
+}
+inline void debugPut(Oracle &o, uint32_t pixel, uint8_t r, uint8_t g, uint8_t b) {
+    uint8_t *p = &o.debugOutput[4 * (size_t)pixel];
+    p[0] = r; p[1] = g; p[2] = b; p[3] = 255;
+}
+void debugClearBuffer(Oracle &o) {  // debug.cl:16-20 over FrameW*FrameH (resources.go:362-375)
+    for (size_t i = 0; i < (size_t)o.frameW * o.frameH; i++) debugPut(o, (uint32_t)i, 0, 0, 0);
+}
+void debugRayIntersectionDepth(Oracle &o, const pc_block_request &req, int buf) {  // debug.cl:23-48, resources.go:378-421
+    debugClearBuffer(o);
+    float maxDepth = 1.0f;
+    for (const Intersection &i : o.intersections)
+        if (i.wuvt.w != FLT_MAX && i.wuvt.w > maxDepth) maxDepth = i.wuvt.w;
+    const int n = (int)((size_t)req.frame_w * req.block_h);
+    for (int globalId = 0; globalId < n && globalId < o.numRays[buf]; globalId++) {
+        uint32_t pixelIndex = o.paths[globalId].pixelIndex;
+        float hitDist = o.intersections[globalId].wuvt.w;
+        if (!o.hitFlags[globalId] || hitDist == FLT_MAX) { debugPut(o, pixelIndex, 0, 0, 0); continue; }
+        uint8_t sd = (uint8_t)(255.0f * (1.0f - hitDist / (maxDepth + 1.0f)));
+        debugPut(o, pixelIndex, sd, sd, sd);
+    }
+}
+void debugRayIntersectionNormals(Oracle &o, const pc_block_request &req, int buf) {  // debug.cl:51-97, resources.go:424-455
+    debugClearBuffer(o);
+    const int n = (int)((size_t)req.frame_w * req.block_h);
+    for (int globalId = 0; globalId < n && globalId < o.numRays[buf]; globalId++) {
+        uint32_t pixelIndex = o.paths[globalId].pixelIndex;
+        float hitDist = o.intersections[globalId].wuvt.w;
+        if (!o.hitFlags[globalId] || hitDist == FLT_MAX) { debugPut(o, pixelIndex, 0, 0, 0); continue; }
+        Surface surface;
+        surfaceInit(&surface, &o.intersections[globalId], o.sc);
+        f3 inRayDir = -xyz(o.rays[buf][globalId].dir);
+        MaterialNode materialNode;
+        u2 rndState = u2{(uint32_t)globalId, (uint32_t)globalId};
+        f3 bxdfTint;
+        MatStats ms;
+        matSelectNode(&o.paths[globalId], &surface, inRayDir, &materialNode, &bxdfTint, o.sc, &rndState, &ms);  // may set dispersion bits
+        f3 val = (surface.normal + 1.0f) * 255.0f * 0.5f;
+        debugPut(o, pixelIndex, (uint8_t)val.x, (uint8_t)val.y, (uint8_t)val.z);
+    }
+}
+void debugEmissiveSamples(Oracle &o, const pc_block_request &req, uint32_t maskOccluded, uint32_t maskNotOccluded) {  // debug.cl:100-126
+    debugClearBuffer(o);
+    const int n = (int)((size_t)req.frame_w * req.block_h);
+    for (int globalId = 0; globalId < n && globalId < o.numRays[2]; globalId++) {
+        uint32_t pathIndex = (uint32_t)o.rays[2][globalId].dir.w;
+        uint32_t pixelIndex = o.paths[pathIndex].pixelIndex;
+        if ((maskOccluded && o.hitFlags[globalId]) || (maskNotOccluded && !o.hitFlags[globalId])) { debugPut(o, pixelIndex, 0, 0, 0); continue; }
+        f3 val = debugToneMapAndGammaCorrect(xyz(o.emissiveSamples[globalId]));
+        debugPut(o, pixelIndex, (uint8_t)val.x, (uint8_t)val.y, (uint8_t)val.z);
+    }
+}
+void debugThroughput(Oracle &o, const pc_block_request &req) {  // debug.cl:129-140: every path of the block, no ray count
+    debugClearBuffer(o);
+    const size_t n = (size_t)req.frame_w * req.block_h;
+    for (size_t globalId = 0; globalId < n; globalId++) {
+        f3 val = debugToneMapAndGammaCorrect(o.paths[globalId].throughput);
+        debugPut(o, o.paths[globalId].pixelIndex, (uint8_t)val.x, (uint8_t)val.y, (uint8_t)val.z);
+    }
+}
+void debugAccumulator(Oracle &o, const pc_block_request &req) {  // debug.cl:143-154: indexed by work-item, not by pixelIndex
+    debugClearBuffer(o);
+    const size_t n = (size_t)req.frame_w * req.block_h;
+    float sampleWeight = 1.0f / (float)(req.accumulated_samples + req.samples_per_pixel);  // resources.go:509
+    for (size_t globalId = 0; globalId < n; globalId++) {
+        f3 val = debugToneMapAndGammaCorrect(xyz(o.traceAcc[globalId]) * sampleWeight);
+        debugPut(o, (uint32_t)globalId, (uint8_t)val.x, (uint8_t)val.y, (uint8_t)val.z);
+    }
+}
+struct DebugSink {
+    uint32_t flags = 0;
+    uint8_t *frames = nullptr;
+    uint64_t cap = 0;
+    pc_debug_frame *infos = nullptr;
+    uint32_t infosCap = 0, n = 0;
+    bool capture = false;
+    int overflow = 0;
+};
+void debugDump(Oracle &o, DebugSink &d, uint32_t flag, uint32_t bounce) {  // dumpDebugBuffer (pipeline.go:259-277)
+    if (!d.capture) return;
+    const uint64_t bytes = (uint64_t)o.frameW * o.frameH * 4;
+    if ((uint64_t)(d.n + 1) * bytes > d.cap || d.n >= d.infosCap) { d.overflow = 1; return; }
+    memcpy(d.frames + (uint64_t)d.n * bytes, o.debugOutput.data(), bytes);
+    d.infos[d.n] = pc_debug_frame{flag, bounce};
+    d.n++;
+}
+
+// Tracer.Trace (tracer.go:194-247) + MonteCarloIntegrator (pipeline.go:94-213); dbg adds the debug stages
+int traceImpl(Oracle &o, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats, DebugSink *dbg) {
+    if (!o.sc.loaded) return PC_ERR_NO_SCENE_DATA;
+    if (o.frameW != req->frame_w || o.frameH != req->frame_h) return PC_ERR_NO_FRAME;
+    const size_t per_sample = 1 + (size_t)req->num_bounces;
+    if (seeds && n_seeds < per_sample * req->samples_per_pixel) return PC_ERR_INVALID_ARGUMENT;
+    auto t0 = std::chrono::steady_clock::now();
+    memset(&o.stats, 0, sizeof(o.stats));
+    const size_t px = (size_t)req->frame_w * req->frame_h;
+    if (req->accumulated_samples == 0)  // pipeline.Reset -> ClearFrameAccumulator (tracer.go:208-213)
+        std::fill(o.frameAcc.begin(), o.frameAcc.begin() + px, f4{0, 0, 0, 0});
+    std::fill(o.traceAcc.begin(), o.traceAcc.begin() + px, f4{0, 0, 0, 0});  // tracer.go:215
+    uint64_t own = 0x501A2150ull + req->seed;
+    const uint32_t df = dbg ? dbg->flags : 0u;
+    for (uint32_t sample = 0; sample < req->samples_per_pixel; sample++) {
+        if (dbg) dbg->capture = sample + 1 == req->samples_per_pixel;  // the reference overwrites its PNGs every sample
+        const uint32_t *ss = seeds ? seeds + per_sample * sample : nullptr;
+        req->seed = ss ? ss[0] : nextSeed(own);  // tracer.go:222
+        generatePrimaryRays(o, *req, req->seed);
+        int activeRayBuf = 0;
+        rayIntersectionQuery(o, activeRayBuf);  // CPU device: pipeline.go:110
+        if (df & PC_DEBUG_PRIMARY_DEPTH) { debugRayIntersectionDepth(o, *req, activeRayBuf); debugDump(o, *dbg, PC_DEBUG_PRIMARY_DEPTH, 0); }        // :113-119
+        if (df & PC_DEBUG_PRIMARY_NORMALS) { debugRayIntersectionNormals(o, *req, activeRayBuf); debugDump(o, *dbg, PC_DEBUG_PRIMARY_NORMALS, 0); }  // :120-126
+        for (uint32_t bounce = 0; bounce < req->num_bounces; bounce++) {
+            if (o.sc.sceneDiffuseMatIndex != -1) shadeMisses(o, activeRayBuf, bounce == 0);  // :134-143
+            uint32_t shadeSeed = ss ? ss[1 + bounce] : nextSeed(own);                        // :146
+            shadeHits(o, activeRayBuf, bounce, req->min_bounces_for_rr, shadeSeed);
+            if (df & PC_DEBUG_THROUGHPUT) { debugThroughput(o, *req); debugDump(o, *dbg, PC_DEBUG_THROUGHPUT, bounce); }  // :151-157
+            rayIntersectionTest(o, 2);       // :160
+            accumulateEmissiveSamples(o, 2); // :165
+            if (df & PC_DEBUG_ALL_EMISSIVE) { debugEmissiveSamples(o, *req, 0, 0); debugDump(o, *dbg, PC_DEBUG_ALL_EMISSIVE, bounce); }            // :170-176
+            if (df & PC_DEBUG_VISIBLE_EMISSIVE) { debugEmissiveSamples(o, *req, 1, 0); debugDump(o, *dbg, PC_DEBUG_VISIBLE_EMISSIVE, bounce); }    // :178-184
+            if (df & PC_DEBUG_OCCLUDED_EMISSIVE) { debugEmissiveSamples(o, *req, 0, 1); debugDump(o, *dbg, PC_DEBUG_OCCLUDED_EMISSIVE, bounce); }  // :186-192
+            if (df & PC_DEBUG_ACCUMULATOR) { debugAccumulator(o, *req); debugDump(o, *dbg, PC_DEBUG_ACCUMULATOR, bounce); }                        // :194-200
+            if (bounce + 1 < req->num_bounces) {  // :203-209
+                activeRayBuf = 1 - activeRayBuf;
+                rayIntersectionQuery(o, activeRayBuf);
+            }
+        }
+        req->accumulated_samples++;  // tracer.go:240
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    o.stats.block_w = req->block_w;
+    o.stats.block_h = req->block_h;
+    o.stats.render_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+    if (stats) *stats = o.stats;
+    return dbg && dbg->overflow ? PC_ERR_INVALID_ARGUMENT : 0;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -1177,6 +1321,7 @@ int po_resize(void *h, uint32_t w, uint32_t hgt) {
     o.traceAcc.assign(px, f4{0, 0, 0, 0});
     o.frameAcc.assign(px, f4{0, 0, 0, 0});
     o.frameBuffer.assign(px * 4, 0);
+    o.debugOutput.assign(px * 4, 0);
     o.wantOcc.assign(px, 0); o.wantInd.assign(px, 0);
     o.occRay.assign(px, Ray{}); o.indRay.assign(px, Ray{});
     o.occSample.assign(px, f4{0, 0, 0, 0});
@@ -1210,45 +1355,18 @@ int po_set_camera(void *h, const float eye[3], const float frustum[16]) {
     return 0;
 }
 
-// Tracer.Trace (tracer.go:194-247) + MonteCarloIntegrator (pipeline.go:94-213)
 int po_trace(void *h, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats) {
-    Oracle &o = *(Oracle *)h;
-    if (!o.sc.loaded) return PC_ERR_NO_SCENE_DATA;
-    if (o.frameW != req->frame_w || o.frameH != req->frame_h) return PC_ERR_NO_FRAME;
-    const size_t per_sample = 1 + (size_t)req->num_bounces;
-    if (seeds && n_seeds < per_sample * req->samples_per_pixel) return PC_ERR_INVALID_ARGUMENT;
-    auto t0 = std::chrono::steady_clock::now();
-    memset(&o.stats, 0, sizeof(o.stats));
-    const size_t px = (size_t)req->frame_w * req->frame_h;
-    if (req->accumulated_samples == 0)  // pipeline.Reset -> ClearFrameAccumulator (tracer.go:208-213)
-        std::fill(o.frameAcc.begin(), o.frameAcc.begin() + px, f4{0, 0, 0, 0});
-    std::fill(o.traceAcc.begin(), o.traceAcc.begin() + px, f4{0, 0, 0, 0});  // tracer.go:215
-    uint64_t own = 0x501A2150ull + req->seed;
-    for (uint32_t sample = 0; sample < req->samples_per_pixel; sample++) {
-        const uint32_t *ss = seeds ? seeds + per_sample * sample : nullptr;
-        req->seed = ss ? ss[0] : nextSeed(own);  // tracer.go:222
-        generatePrimaryRays(o, *req, req->seed);
-        int activeRayBuf = 0;
-        rayIntersectionQuery(o, activeRayBuf);  // CPU device: pipeline.go:110
-        for (uint32_t bounce = 0; bounce < req->num_bounces; bounce++) {
-            if (o.sc.sceneDiffuseMatIndex != -1) shadeMisses(o, activeRayBuf, bounce == 0);  // :134-143
-            uint32_t shadeSeed = ss ? ss[1 + bounce] : nextSeed(own);                        // :146
-            shadeHits(o, activeRayBuf, bounce, req->min_bounces_for_rr, shadeSeed);
-            rayIntersectionTest(o, 2);       // :160
-            accumulateEmissiveSamples(o, 2); // :165
-            if (bounce + 1 < req->num_bounces) {  // :203-209
-                activeRayBuf = 1 - activeRayBuf;
-                rayIntersectionQuery(o, activeRayBuf);
-            }
-        }
-        req->accumulated_samples++;  // tracer.go:240
-    }
-    auto t1 = std::chrono::steady_clock::now();
-    o.stats.block_w = req->block_w;
-    o.stats.block_h = req->block_h;
-    o.stats.render_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
-    if (stats) *stats = o.stats;
-    return 0;
+    return traceImpl(*(Oracle *)h, req, seeds, n_seeds, stats, nullptr);
+}
+
+// MonteCarloIntegrator(debugFlags): same call shape as pc_trace_debug (include/polaris_cuda.h)
+int po_trace_debug(void *h, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, uint32_t debug_flags, uint8_t *frames_out,
+                   uint64_t frames_cap_bytes, pc_debug_frame *infos, uint32_t infos_cap, uint32_t *n_frames, pc_stats *stats) {
+    DebugSink d;
+    d.flags = debug_flags; d.frames = frames_out; d.cap = frames_cap_bytes; d.infos = infos; d.infosCap = infos_cap;
+    int rc = traceImpl(*(Oracle *)h, req, seeds, n_seeds, stats, &d);
+    if (n_frames) *n_frames = d.n;
+    return rc;
 }
 
 // Tracer.MergeOutput -> aggregateAccumulator (accumulator.cl:13-19, resources.go:108-124)

@@ -28,6 +28,7 @@ _SYMS = [
     ("pr_upload_scene", ctypes.c_int, [vp, _P(SceneView)]),
     ("pr_set_camera", ctypes.c_int, [vp, _P(f32), _P(f32)]),
     ("pr_trace", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, _P(Stats)]),
+    ("pr_trace_debug", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, u32, vp, u64, vp, u32, _P(u32), _P(Stats)]),
     ("pr_merge_output", ctypes.c_int, [vp, vp, _P(BlockRequest)]),
     ("pr_sync_framebuffer", ctypes.c_int, [vp, _P(BlockRequest), vp]),
     ("pr_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),

@@ -68,6 +68,21 @@ BUF_EMISSIVE_SAMPLES, BUF_TRACE_ACCUMULATOR, BUF_FRAME_ACCUMULATOR, BUF_FRAME_BU
 OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE = 0, 1, 2, 3, 4, 5, 6, 7
 K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY, K_TRACE = 0, 1, 2, 3, 4, 5
 KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query", "k_trace"]
+# pc_debug_flag == opencl.DebugFlag (tracer/opencl/pipeline.go:17-30)
+DEBUG_PRIMARY_DEPTH, DEBUG_PRIMARY_NORMALS, DEBUG_ALL_EMISSIVE, DEBUG_VISIBLE_EMISSIVE = 2, 4, 8, 16
+DEBUG_OCCLUDED_EMISSIVE, DEBUG_THROUGHPUT, DEBUG_ACCUMULATOR, DEBUG_FRAMEBUFFER = 32, 64, 128, 256
+DEBUG_ALL_STAGES = 2 | 4 | 8 | 16 | 32 | 64 | 128
+# file names the reference gives the dumps (pipeline.go:115-196)
+DEBUG_FILE_NAMES = {2: "debug-primary-intersection-depth.png", 4: "debug-primary-intersection-normals.png", 8: "debug-emissive-all-%03d.png",
+                    16: "debug-emissive-vis-%03d.png", 32: "debug-emissive-occ-%03d.png", 64: "debug-throughput-%03d.png",
+                    128: "debug-accumulator-%03d.png"}
+DEBUG_FRAME_DTYPE = np.dtype([("flag", np.uint32), ("bounce", np.uint32)])
+
+
+def debug_frame_count(flags: int, num_bounces: int) -> int:
+    return bin(flags & 6).count("1") + num_bounces * bin(flags & (8 | 16 | 32 | 64 | 128)).count("1")
+
+
 # pc_status
 OK = 0
 ERR_INVALID_ARGUMENT, ERR_NO_DEVICE, ERR_ALLOC, ERR_COPY_TO_DEVICE, ERR_COPY_TO_HOST, ERR_KERNEL = 1, 2, 3, 4, 5, 6
@@ -106,6 +121,8 @@ SYMBOLS = [
     ("pc_trace_rows", ctypes.c_int, [vp, _P(BlockRequest), _P(vp), _P(u64)]),
     ("pc_sync_framebuffer", ctypes.c_int, [vp, _P(BlockRequest), vp]),
     ("pc_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),
+    ("pc_debug_frame_count", u32, [u32, u32]),
+    ("pc_trace_debug", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, u32, vp, u64, vp, u32, _P(u32), _P(Stats)]),
     ("pc_debug_intersect", ctypes.c_int, [vp, vp, u32, ctypes.c_int, vp, vp]),
     ("pc_debug_bxdf", ctypes.c_int, [vp, vp, u32, vp]),
     ("pc_debug_rng", ctypes.c_int, [vp, vp, u32, u32, vp]),

@@ -90,7 +90,7 @@ struct pc_tracer {
     uint64_t sceneEpoch = 0, cameraEpoch = 0;
     // frame
     uint32_t W = 0, H = 0;
-    DevBuf traceAcc, frameAcc, frameBuf, seedsDev, scratch, params;
+    DevBuf traceAcc, frameAcc, frameBuf, seedsDev, scratch, params, debugBuf;
     // Sample chains.  The samples of a block request are independent given their seeds, and one sample's
     // launches (a few hundred thousand rays each at the BASELINE sizes) leave the machine idle in their
     // tails, so chain c traces samples c, c+nChains, ... with its own ray / path / hit state on its own
@@ -192,8 +192,70 @@ struct LaunchTimer {
     }
 };
 
+// ---- debug stages (pipeline.go:113-200, resources.go:362-520): pc_trace_debug ----
+struct DebugSink {
+    uint32_t flags = 0;
+    uint8_t *frames = nullptr;
+    uint64_t cap = 0;
+    pc_debug_frame *infos = nullptr;
+    uint32_t infosCap = 0, n = 0;
+    bool capture = false;  // the reference overwrites its PNG files every sample: only the last sample's dumps survive
+    int overflow = 0;
+    uint64_t launches = 0;
+    uint32_t sampleIndex = 0;  // tracer.go:240 bumps AccumulatedSamples after every sample
+};
+
+// dumpDebugBuffer (pipeline.go:259-277): the debug buffer -> the caller's next frame slot, ordered on the stream
+static void debug_dump(pc_tracer *tr, cudaStream_t s, DebugSink &d, uint32_t flag, uint32_t bounce) {
+    if (!d.capture) return;
+    const uint64_t bytes = (uint64_t)tr->W * tr->H * 4;
+    if ((uint64_t)(d.n + 1) * bytes > d.cap || d.n >= d.infosCap) { d.overflow = 1; return; }
+    cudaMemcpyAsync(d.frames + (uint64_t)d.n * bytes, tr->debugBuf.p, bytes, cudaMemcpyDeviceToHost, s);
+    d.infos[d.n].flag = flag;
+    d.infos[d.n].bounce = bounce;
+    d.n++;
+}
+
+static void debug_stage(pc_tracer *tr, Chain &ch, const pc_block_request &req, DebugSink &d, uint32_t flag, uint32_t bounce, int a) {
+    cudaStream_t s = ch.stream;
+    const uint32_t px = tr->W * tr->H, n = req.frame_w * req.block_h;
+    const FrameBufs &fb = ch.fb;
+    const TraceCtl *ctl = (const TraceCtl *)ch.ctl.p;
+    uchar4 *out = (uchar4 *)tr->debugBuf.p;
+    uint32_t *maxBits = (uint32_t *)((char *)tr->debugBuf.p + (size_t)px * 4);
+    const int B = 256, G = (int)((n + B - 1) / B);
+    k_debug_clear<<<(px + B - 1) / B, B, 0, s>>>(out, px);  // DebugClearBuffer
+    d.launches += 2;
+    switch (flag) {
+        case PC_DEBUG_PRIMARY_DEPTH: {
+            const uint32_t one = 0x3F800000u;  // maxDepth starts at 1.0 (resources.go:397)
+            cudaMemcpyAsync(maxBits, &one, 4, cudaMemcpyHostToDevice, s);
+            k_debug_max_depth<<<(px + B - 1) / B, B, 0, s>>>(fb.hits, px, maxBits);
+            k_debug_depth<<<G, B, 0, s>>>(ctl, a, fb.paths, fb.hitFlags, fb.hits, maxBits, out, n);
+            d.launches++;
+            break;
+        }
+        case PC_DEBUG_PRIMARY_NORMALS:
+            k_debug_normals<<<G, B, 0, s>>>(tr->sc, ctl, a, fb.rays[a], fb.paths, fb.hitFlags, fb.hits, out, n);
+            break;
+        case PC_DEBUG_ALL_EMISSIVE: case PC_DEBUG_VISIBLE_EMISSIVE: case PC_DEBUG_OCCLUDED_EMISSIVE:
+            k_debug_emissive<<<G, B, 0, s>>>(ctl, fb.rays[2], fb.paths, fb.hitFlags, fb.emissiveSamples,
+                                            flag == PC_DEBUG_VISIBLE_EMISSIVE ? 1u : 0u, flag == PC_DEBUG_OCCLUDED_EMISSIVE ? 1u : 0u, out, n);
+            break;
+        case PC_DEBUG_THROUGHPUT:
+            k_debug_throughput<<<G, B, 0, s>>>(fb.paths, out, n);
+            break;
+        case PC_DEBUG_ACCUMULATOR: {
+            const float sampleWeight = 1.0f / (float)(req.accumulated_samples + d.sampleIndex + req.samples_per_pixel);  // resources.go:509
+            k_debug_accumulator<<<G, B, 0, s>>>(sampleWeight, fb.traceAcc, out, n);
+            break;
+        }
+    }
+    debug_dump(tr, s, d, flag, bounce);
+}
+
 template <bool COUNT>
-void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches) {
+void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches, DebugSink *dbg) {
     cudaStream_t s = ch.stream;
     TraceCtl *ctl = (TraceCtl *)ch.ctl.p;
     const uint32_t *seeds = (const uint32_t *)tr->seedsDev.p;
@@ -224,6 +286,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     L++;
     slot++;
     int a = 0;
+    const uint32_t df = dbg ? dbg->flags : 0u;
+    if (df & PC_DEBUG_PRIMARY_DEPTH) debug_stage(tr, ch, req, *dbg, PC_DEBUG_PRIMARY_DEPTH, 0, a);      // pipeline.go:113-119
+    if (df & PC_DEBUG_PRIMARY_NORMALS) debug_stage(tr, ch, req, *dbg, PC_DEBUG_PRIMARY_NORMALS, 0, a);  // :120-126
     for (uint32_t bounce = 0; bounce < nb; bounce++) {
         // ShadePrimaryRayMisses / ShadeIndirectRayMisses + ShadeHits (pipeline.go:134-146)
         {
@@ -232,7 +297,8 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
                                                             perSample, bounce, req.min_bounces_for_rr, a, tr->optFixQ4);
         }
         L++;
-        if (tr->optFuse && !tr->optRefOrder && bounce + 1 < nb) {
+        if (df & PC_DEBUG_THROUGHPUT) debug_stage(tr, ch, req, *dbg, PC_DEBUG_THROUGHPUT, bounce, a);  // :151-157
+        if (tr->optFuse && !tr->optRefOrder && bounce + 1 < nb && !dbg) {
             // RayIntersectionTest(2) + AccumulateEmissiveSamples(2) and the next bounce's RayIntersectionQuery
             // (pipeline.go:160-165, :203-209) are independent: one persistent launch covers both
             a = 1 - a;
@@ -246,12 +312,16 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
         if (tr->optRefOrder)
-            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot);
         else
-            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, ctl, slot);
+            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot);
         }
         L++;
         slot++;
+        if (df & PC_DEBUG_ALL_EMISSIVE) debug_stage(tr, ch, req, *dbg, PC_DEBUG_ALL_EMISSIVE, bounce, a);            // :170-176
+        if (df & PC_DEBUG_VISIBLE_EMISSIVE) debug_stage(tr, ch, req, *dbg, PC_DEBUG_VISIBLE_EMISSIVE, bounce, a);    // :178-184
+        if (df & PC_DEBUG_OCCLUDED_EMISSIVE) debug_stage(tr, ch, req, *dbg, PC_DEBUG_OCCLUDED_EMISSIVE, bounce, a);  // :186-192
+        if (df & PC_DEBUG_ACCUMULATOR) debug_stage(tr, ch, req, *dbg, PC_DEBUG_ACCUMULATOR, bounce, a);              // :194-200
         if (bounce + 1 < nb) {  // pipeline.go:203-209
             a = 1 - a;
             LaunchTimer lt(tr, PC_K_QUERY);
@@ -266,9 +336,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     *launches = L;
 }
 
-void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches) {
-    if (tr->optCounters) record_sample_t<true>(tr, ch, req, sampleStride, launches);
-    else record_sample_t<false>(tr, ch, req, sampleStride, launches);
+void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches, DebugSink *dbg = nullptr) {
+    if (tr->optCounters) record_sample_t<true>(tr, ch, req, sampleStride, launches, dbg);
+    else record_sample_t<false>(tr, ch, req, sampleStride, launches, dbg);
 }
 
 // Enqueue perChain[c] samples on every chain c < nChains: fork the chain streams off the handle's stream,
@@ -458,7 +528,7 @@ void pc_destroy(pc_tracer *tr) {
         drop_graph(tr);
         DevBuf *all[] = {&tr->bvh, &tr->inst, &tr->mats, &tr->texData, &tr->texMeta, &tr->verts, &tr->normals, &tr->uvs,
                          &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->traceAcc, &tr->frameAcc,
-                         &tr->frameBuf, &tr->seedsDev, &tr->scratch, &tr->params};
+                         &tr->frameBuf, &tr->seedsDev, &tr->scratch, &tr->params, &tr->debugBuf};
         release_chain_buffers(tr);
         for (int c = 0; c < MAX_CHAINS; c++) {
             tr->chain[c].ctl.release();
@@ -609,8 +679,8 @@ int pc_set_camera(pc_tracer *tr, const float eye[3], const float frustum[16]) {
     return 0;
 }
 
-// Tracer.Trace (tracer.go:194-247)
-int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats) {
+// Tracer.Trace (tracer.go:194-247); dbg != nullptr: MonteCarloIntegrator(debugFlags) -- one chain, direct launches
+static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats, DebugSink *dbg) {
     int rc = enter(tr);
     if (rc) return rc;
     if (!req) return fail(tr, PC_ERR_INVALID_ARGUMENT, "null block request");
@@ -647,8 +717,9 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     hp.frameW = req->frame_w; hp.blockY = req->block_y; hp.blockH = req->block_h; hp.pad = 0;
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->params.p, &hp, sizeof(hp), cudaMemcpyHostToDevice, s));
     // ---- sample chains: chain c traces samples c, c + nc, c + 2 nc, ...
-    int nc = tr->optTimers ? 1 : tr->optChains;
+    int nc = (tr->optTimers || dbg) ? 1 : tr->optChains;
     if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
+    if (dbg) CU(tr, PC_ERR_ALLOC, tr->debugBuf.bytes >= (size_t)tr->W * tr->H * 4 + 16 ? cudaSuccess : tr->debugBuf.alloc((size_t)tr->W * tr->H * 4 + 16));
     if ((rc = ensure_chains(tr, nc))) return rc;
     static const uint32_t kChainIndex[MAX_CHAINS] = {0, 1, 2, 3, 4, 5, 6, 7};
     for (int c = 0; c < nc; c++) {
@@ -666,7 +737,18 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     if (spp > 0) {
         tr->timerClass.clear();
         uint32_t done = 0;
-        if (tr->optGraph && !tr->optTimers && spp >= (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc)) {
+        if (dbg) {
+            for (; done < spp; done++) {
+                dbg->capture = done + 1 == spp;
+                dbg->sampleIndex = done;
+                record_sample(tr, tr->chain[0], *req, 1u, &perSampleLaunches, dbg);
+            }
+            if (cudaGetLastError() != cudaSuccess) {
+                tr->dead = true;
+                return fail(tr, PC_ERR_KERNEL, "debug stage launch failed");
+            }
+        }
+        if (tr->optGraph && !tr->optTimers && !dbg && spp >= (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc)) {
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
@@ -733,7 +815,7 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     st.device_time_ns = (uint64_t)((double)ms * 1e6);
     st.query_rays = hc.stats[ST_QUERY_RAYS];
     st.occlusion_rays = hc.stats[ST_OCCLUSION_RAYS];
-    st.kernel_launches = launches + perSampleLaunches * spp;
+    st.kernel_launches = launches + perSampleLaunches * spp + (dbg ? dbg->launches : 0);
     st.nodes_tested = hc.stats[ST_NODES];
     st.tris_tested = hc.stats[ST_TRIS];
     st.instances_entered = hc.stats[ST_INSTANCES];
@@ -753,7 +835,32 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t
     }
     st.render_time_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     if (stats) *stats = st;
+    if (dbg && dbg->overflow) return fail(tr, PC_ERR_INVALID_ARGUMENT, "debug frames do not fit: need %u frames of %zu bytes", pc_debug_frame_count(dbg->flags, req->num_bounces), (size_t)tr->W * tr->H * 4);
     return 0;
+}
+
+int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats) {
+    return trace_common(tr, req, seeds, n_seeds, stats, nullptr);
+}
+
+uint32_t pc_debug_frame_count(uint32_t debug_flags, uint32_t num_bounces) {
+    const uint32_t once = PC_DEBUG_PRIMARY_DEPTH | PC_DEBUG_PRIMARY_NORMALS;
+    const uint32_t perBounce = PC_DEBUG_ALL_EMISSIVE | PC_DEBUG_VISIBLE_EMISSIVE | PC_DEBUG_OCCLUDED_EMISSIVE | PC_DEBUG_THROUGHPUT | PC_DEBUG_ACCUMULATOR;
+    return (uint32_t)__builtin_popcount(debug_flags & once) + num_bounces * (uint32_t)__builtin_popcount(debug_flags & perBounce);
+}
+
+// MonteCarloIntegrator(debugFlags) (pipeline.go:94-213)
+int pc_trace_debug(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, uint32_t debug_flags, uint8_t *frames_out,
+                   uint64_t frames_cap_bytes, pc_debug_frame *infos, uint32_t infos_cap, uint32_t *n_frames, pc_stats *stats) {
+    if (n_frames) *n_frames = 0;
+    if (!tr) return PC_ERR_INVALID_ARGUMENT;
+    if ((!frames_out || !infos) && pc_debug_frame_count(debug_flags, req ? req->num_bounces : 0))
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "null debug frame buffer");
+    DebugSink d;
+    d.flags = debug_flags; d.frames = frames_out; d.cap = frames_cap_bytes; d.infos = infos; d.infosCap = infos_cap;
+    int rc = trace_common(tr, req, seeds, n_seeds, stats, &d);
+    if (n_frames) *n_frames = d.n;
+    return rc;
 }
 
 int pc_get_stats(pc_tracer *tr, pc_stats *stats) {

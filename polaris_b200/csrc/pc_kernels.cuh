@@ -922,6 +922,81 @@ __global__ void k_tonemap(const float4 *acc, uchar4 *fb, size_t n, float sampleW
 }
 
 // ------------------------------------------------------------------------------------------------
+// kernels/debug.cl:16-156 -- the reference's debug visualisations (pc_trace_debug).  One thread per work-item,
+// plain launches: a debugging aid, not a fast path.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uchar4 debugToneMap(float3 sample) {  // debugToneMapAndGammaCorrect (debug.cl:8-13)
+    sample = sample * 1.0f;  // DEBUG_TONEMAP_EXPOSURE
+    float3 mapped = sample / (sample + 1.0f);
+    const float e = 1.0f / 2.2f;
+    float3 v = f3(cl_clamp(powf(mapped.x, e), 0.0f, 1.0f), cl_clamp(powf(mapped.y, e), 0.0f, 1.0f), cl_clamp(powf(mapped.z, e), 0.0f, 1.0f)) * 255.0f;
+    return make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z, 255);
+}
+__global__ void k_debug_clear(uchar4 *out, uint32_t n) {  // debugClearBuffer (:16-20)
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_uchar4(0, 0, 0, 255);
+}
+// max over the whole intersection buffer of the finite hit distances, start value 1 (resources.go:398-404); positive
+// floats order like their bit patterns
+__global__ void k_debug_max_depth(const HitRec *hits, uint32_t n, uint32_t *maxBits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float t = 1.0f;
+    if (i < n) {
+        float w = hits[i].wuvt.w;
+        if (w != FLT_MAX && w > 1.0f) t = w;
+    }
+    for (int d = 16; d > 0; d >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, d));
+    if (lane_id() == 0) atomicMax(maxBits, __float_as_uint(t));
+}
+__global__ void k_debug_depth(const TraceCtl *ctl, int a, const PathRec *paths, const uint32_t *hitFlags, const HitRec *hits,
+                              const uint32_t *maxBits, uchar4 *out, uint32_t n) {  // debugRayIntersectionDepth (:23-48)
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n || (int)g >= ctl->numRays[a]) return;
+    const uint32_t pixel = paths[g].meta.x;
+    const float hitDist = hits[g].wuvt.w, maxDepth = __uint_as_float(*maxBits);
+    if (!hitFlags[g] || hitDist == FLT_MAX) { out[pixel] = make_uchar4(0, 0, 0, 255); return; }
+    const unsigned char sd = (unsigned char)(255.0f * (1.0f - hitDist / (maxDepth + 1.0f)));
+    out[pixel] = make_uchar4(sd, sd, sd, 255);
+}
+__global__ void k_debug_normals(DScene sc, const TraceCtl *ctl, int a, const Ray *rays, PathRec *paths, const uint32_t *hitFlags,
+                                const HitRec *hits, uchar4 *out, uint32_t n) {  // debugRayIntersectionNormals (:51-97)
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n || (int)g >= ctl->numRays[a]) return;
+    const uint32_t pixel = paths[g].meta.x;
+    const HitRec h = hits[g];
+    if (!hitFlags[g] || h.wuvt.w == FLT_MAX) { out[pixel] = make_uchar4(0, 0, 0, 255); return; }
+    Surface surface;
+    surfaceInit(surface, h.wuvt, h.meta.y, sc);
+    uint2 rnd = make_uint2(g, g);
+    float3 tint = f3(1.0f, 1.0f, 1.0f);
+    uint32_t flags = paths[g].meta.y;
+    const uint32_t before = flags;
+    matSelectNode(flags, surface, tint, sc, rnd);  // bump / normal maps perturb surface.normal; disperse sets path bits
+    if (flags != before) paths[g].meta.y = flags;
+    const float3 v = (surface.normal + 1.0f) * 255.0f * 0.5f;
+    out[pixel] = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z, 255);
+}
+__global__ void k_debug_emissive(const TraceCtl *ctl, const Ray *rays, const PathRec *paths, const uint32_t *hitFlags,
+                                 const float4 *emissiveSamples, uint32_t maskOccluded, uint32_t maskNotOccluded, uchar4 *out,
+                                 uint32_t n) {  // debugEmissiveSamples (:100-126)
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n || (int)g >= ctl->numRays[2]) return;
+    const uint32_t pixel = paths[(uint32_t)rays[g].dir.w].meta.x;
+    if ((maskOccluded && hitFlags[g]) || (maskNotOccluded && !hitFlags[g])) { out[pixel] = make_uchar4(0, 0, 0, 255); return; }
+    out[pixel] = debugToneMap(xyz(emissiveSamples[g]));
+}
+__global__ void k_debug_throughput(const PathRec *paths, uchar4 *out, uint32_t n) {  // debugThroughput (:129-140)
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    out[paths[g].meta.x] = debugToneMap(xyz(paths[g].throughput));
+}
+__global__ void k_debug_accumulator(float sampleWeight, const float4 *acc, uchar4 *out, uint32_t n) {  // debugAccumulator (:143-154)
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    out[g] = debugToneMap(xyz(acc[g]) * sampleWeight);  // indexed by work-item, not by pixelIndex, like the reference
+}
+
+// ------------------------------------------------------------------------------------------------
 // test hooks
 // ------------------------------------------------------------------------------------------------
 struct BxdfIn { float n[3]; uint32_t matNode; float in[3], p0; float out[3], p1; float rnd[2], uv[2]; };

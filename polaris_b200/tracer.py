@@ -195,6 +195,25 @@ class _HandleTracer(Tracer):
         self._stats.device = st.as_dict()
         return dt
 
+    def trace_debug(self, block_req, seeds, debug_flags):
+        """Trace with opencl.DebugFlag stages (pipeline.go:17-30,113-200).  Returns [(flag, bounce, rgba (H, W, 4) uint8)]
+        for the last sample, in the order the reference writes its debug-*.png files."""
+        self._commit_changes()
+        if not self._has_scene:
+            raise ErrNoSceneData(_lib.ERR_NO_SCENE_DATA, "no scene data uploaded")
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        w, h = block_req.frame_w, block_req.frame_h
+        n = _lib.debug_frame_count(debug_flags, block_req.num_bounces)
+        frames = np.zeros((max(n, 1), h, w, 4), dtype=np.uint8)
+        infos = np.zeros(max(n, 1), dtype=_lib.DEBUG_FRAME_DTYPE)
+        got = ctypes.c_uint32(0)
+        st = Stats()
+        self._check(self._fn("trace_debug")(self._h, ctypes.byref(block_req), seeds.ctypes.data, seeds.size, int(debug_flags),
+                                            frames.ctypes.data, frames.nbytes, infos.ctypes.data, len(infos), ctypes.byref(got),
+                                            ctypes.byref(st)))
+        self._stats.device = st.as_dict()
+        return [(int(infos[i]["flag"]), int(infos[i]["bounce"]), frames[i]) for i in range(got.value)]
+
     def merge_output(self, other, block_req):
         if type(other) is not type(self):
             raise ErrUnsupportedTracer(_lib.ERR_UNSUPPORTED_TRACER, "merge failed: unsupported tracer instance")

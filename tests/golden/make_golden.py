@@ -97,8 +97,31 @@ def main():
         ref = C.setup(ref_binding.RefTracer(), sc, *CONFIGS[key])
         np.savez_compressed(os.path.join(HERE, f"bxdf_{key}.npz"), records=recs, out=ref.debug_bxdf(recs), scene_sha256=np.array(scene_digest(sc)))
         ref.close()
+    make_debug()
     print("golden vectors written to", HERE)
 
 
+DEBUG_BOUNCES = 3
+
+
+def make_debug():
+    """debug pipeline stages (kernels/debug.cl + pipeline.go:113-200) from the reference's kernels: 2 + 5 x bounces frames"""
+    for key in ("c2", "c4"):
+        w, h = CONFIGS[key]
+        sc = C.small_scene(key, w, h)
+        ref = C.setup(ref_binding.RefTracer(), sc, w, h)
+        seeds = T.splitmix_seeds(60 + int(key[1]), SPP * (1 + DEBUG_BOUNCES))
+        frames = ref.trace_debug(T.make_block_request(w, h, spp=SPP, num_bounces=DEBUG_BOUNCES), seeds, _lib.DEBUG_ALL_STAGES)
+        np.savez_compressed(os.path.join(HERE, f"debug_{key}.npz"), scene_sha256=np.array(scene_digest(sc)), seeds=seeds,
+                            flags=np.array([f for f, _, _ in frames], np.uint32), bounces=np.array([b for _, b, _ in frames], np.uint32),
+                            frames=np.stack([a for _, _, a in frames]),
+                            path_flags=ref.read_buffer(_lib.BUF_PATHS, w * h, _lib.PATH_DTYPE)["flags"].copy())
+        print(f"debug_{key}: {len(frames)} frames of {w}x{h}")
+        ref.close()
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-debug" in sys.argv:
+        make_debug()
+    else:
+        main()

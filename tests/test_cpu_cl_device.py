@@ -16,7 +16,7 @@ def test_embedded_program_and_portability_rewrite():
     raw, port = D.program_source(portable=False), D.program_source()
     kernels = set(re.findall(rb"__kernel\s+void\s+(\w+)", raw))
     assert set(k.encode() for k in D._KERNELS) <= kernels  # every kernel the host launches exists in the program
-    assert len(kernels) == 17  # 11 on the path + 6 debug (tracer/opencl/kernel_type.go)
+    assert len(kernels) == 17 == len(D._KERNELS)  # 11 on the path + 6 debug (tracer/opencl/kernel_type.go)
     assert b"#include" not in raw  # include-expanded: the GPU box has no /root/reference to resolve them against
     # exactly the 14 functional casts change, line count and everything else stay
     a, b = raw.split(b"\n"), port.split(b"\n")

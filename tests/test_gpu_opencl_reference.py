@@ -13,8 +13,8 @@ discipline by oracle/cl_device.py; the CUDA tracer is called through the C ABI. 
     of them
     beyond 1e-2);
   * converged images: per-pixel RMSE of (OpenCL - CUDA) at N spp equals the Monte-Carlo RMSE of (CUDA seed A -
-    CUDA seed B) at N spp (ratio within 15 %), and the frame means agree within 3e-3 -- i.e. what is left is
-    sampling noise, the estimators have the same expectation.  (A literal per-pixel "RMSE <= 1e-3 of the mean
+    CUDA seed B) at N spp (ratio within 10 %), and the frame means agree within 4.5 standard deviations of that
+    noise (and 1e-2 relative) -- i.e. what is left is sampling noise, the estimators have the same expectation.  (A literal per-pixel "RMSE <= 1e-3 of the mean
     luminance" needs ~1e6 spp: beyond bounce 0 the reference's ray order is atomic arrival order, SURVEY Q13, so
     its noise is independent of ours even with shared seeds; the test states the bound the noise allows.)
 Skipped when the box has no OpenCL driver or oracle/_ref was built without the program text.
@@ -158,8 +158,8 @@ def test_bounce0_radiance_vs_reference_opencl(cld, key, w, h, seed_cfg):
 
 
 def test_converged_image_vs_reference_opencl(cld):
-    w = h = 96
-    spp = 256
+    w = h = 128
+    spp = 512
     sc = C.small_scene("c2", w, h)
     cl, cu = _cl_for(cld, sc, w, h), C.cuda_for(sc, w, h)
     imgs = {}
@@ -174,10 +174,14 @@ def test_converged_image_vs_reference_opencl(cld):
     rmse_ref = np.sqrt(np.mean((lc - la) ** 2))
     rmse_mc = np.sqrt(np.mean((lb - la) ** 2))
     mean = la.mean()
-    print(f"c2 {w}x{h} @ {spp} spp: mean luminance cuda {mean:.5f} opencl {lc.mean():.5f} (rel diff {abs(lc.mean() - mean) / mean:.2e}); "
-          f"RMSE(opencl - cuda) {rmse_ref / mean:.4f} of mean, Monte-Carlo RMSE(cuda A - cuda B) {rmse_mc / mean:.4f} of mean")
-    assert abs(lc.mean() - mean) / mean <= 3e-3
-    assert 0.85 <= rmse_ref / rmse_mc <= 1.15
+    # the difference of two independent frame means has standard deviation rmse_mc / sqrt(pixels)
+    sigma = rmse_mc / np.sqrt(la.size)
+    z = abs(lc.mean() - mean) / sigma
+    print(f"c2 {w}x{h} @ {spp} spp: mean luminance cuda {mean:.5f} opencl {lc.mean():.5f} (rel diff {abs(lc.mean() - mean) / mean:.2e}, "
+          f"{z:.2f} sigma; cuda A vs B: {abs(lb.mean() - mean) / sigma:.2f} sigma); RMSE(opencl - cuda) {rmse_ref / mean:.4f} of mean, "
+          f"Monte-Carlo RMSE(cuda A - cuda B) {rmse_mc / mean:.4f} of mean")
+    assert z <= 4.5 and abs(lc.mean() - mean) / mean <= 1e-2
+    assert 0.9 <= rmse_ref / rmse_mc <= 1.1
     cl.close()
     cu.close()
 
@@ -206,5 +210,24 @@ def test_merge_and_tonemap_vs_reference_opencl(cld):
     print(f"tonemap: {int((d > 0).sum())} of {d.size} bytes differ, max {d.max()} LSB")
     assert d.max() <= 1
     assert (cl.frame_buffer[..., 3] == 255).all()
+    cl.close()
+    cu.close()
+
+
+def test_debug_stages_vs_reference_opencl(cld):
+    """kernels/debug.cl of the reference, compiled by the OpenCL driver, against pc_trace_debug -- bounce 0 only (all
+    seven stages): from bounce 1 on the reference's ray order is atomic arrival order."""
+    w = h = 96
+    sc = C.small_scene("c2", w, h)
+    seeds = T.splitmix_seeds(31, 2)
+    cl, cu = _cl_for(cld, sc, w, h, primary_packets=False), C.cuda_for(sc, w, h)
+    want = cl.trace_debug(T.make_block_request(w, h, spp=1, num_bounces=1), seeds, _lib.DEBUG_ALL_STAGES)
+    got = cu.trace_debug(T.make_block_request(w, h, spp=1, num_bounces=1), seeds, _lib.DEBUG_ALL_STAGES)
+    assert [(f, b) for f, b, _ in got] == [(f, b) for f, b, _ in want] == [(2, 0), (4, 0), (64, 0), (8, 0), (16, 0), (32, 0), (128, 0)]
+    for (f, b, g), (_, _, r) in zip(got, want):
+        d = np.abs(g.astype(np.int32) - r.astype(np.int32)).max(axis=2).reshape(-1)
+        bad = int((d > 1).sum())
+        print(f"debug stage {f}: {int((d > 0).sum())} of {d.size} pixels differ, {bad} by more than 1 LSB")
+        assert bad <= max(2, int(1e-3 * d.size))
     cl.close()
     cu.close()

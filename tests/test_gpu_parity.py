@@ -441,3 +441,75 @@ def test_full_size_row_blocks(key, name):
     print(f"{key}: {checked} pixels in 3 row blocks of the {w}x{h} frame, {len(rays)} rays ({int(hit.sum())} hits) checked; "
           f"{sc.num_triangles} triangles x {len(sc.mesh_instances)} instances")
     cu.close()
+
+
+# --------------------------------------------------------------------------------------------
+# debug pipeline stages (kernels/debug.cl, pipeline.go:113-200) through pc_trace_debug
+# --------------------------------------------------------------------------------------------
+def _assert_frames_close(got, want, what):
+    """RGBA8 frames: bytes within 1 LSB (powf / the shading's transcendental functions differ in the last ulp between CUDA
+    and glibc); pixels whose shading took another branch at a discontinuity are counted and bounded like everywhere else."""
+    assert [(f, b) for f, b, _ in got] == [(f, b) for f, b, _ in want], f"{what}: stage order differs"
+    for (f, b, g), (_, _, w) in zip(got, want):
+        d = np.abs(g.astype(np.int32) - w.astype(np.int32)).max(axis=2).reshape(-1)
+        bad = int((d > 1).sum())
+        allowed = max(2, int(OUTLIER_FRACTION * d.size)) * (1 + b)  # divergent paths stay divergent in later bounces
+        if bad:
+            print(f"{what}: stage {f} bounce {b}: {bad} / {d.size} pixels beyond 1 LSB (allowed {allowed})")
+        assert bad <= allowed, f"{what}: stage {f} bounce {b}: {bad} pixels differ by more than 1 LSB"
+        assert (g[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("key,w,h", [("c2", 96, 96), ("c4", 96, 64)])
+def test_debug_stages_vs_oracle(key, w, h):
+    sc = C.small_scene(key, w, h)
+    spp, nb = 2, 3
+    seeds = T.splitmix_seeds(31, spp * (1 + nb))
+    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h)
+    want = orc.trace_debug(T.make_block_request(w, h, spp=spp, num_bounces=nb), seeds, _lib.DEBUG_ALL_STAGES)
+    got = cu.trace_debug(T.make_block_request(w, h, spp=spp, num_bounces=nb), seeds, _lib.DEBUG_ALL_STAGES)
+    assert len(got) == _lib.debug_frame_count(_lib.DEBUG_ALL_STAGES, nb) == 2 + 5 * nb
+    _assert_frames_close(got, want, key)
+    # depth and normals of the primary hits are pure IEEE arithmetic on bit-exact hit records: identical bytes
+    assert got[0][2].tobytes() == want[0][2].tobytes()
+    if key == "c2":
+        assert got[1][2].tobytes() == want[1][2].tobytes()
+    # the debug pass leaves the same radiance as a plain trace of the same seeds (c2 has no dispersive material, so the
+    # normals stage's matSelectNode changes no path state)
+    if key == "c2":
+        acc_dbg = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
+        cu.set_option(_lib.OPT_SAMPLE_CHAINS, 1)
+        cu.trace(T.make_block_request(w, h, spp=spp, num_bounces=nb), seeds)
+        assert cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes() == acc_dbg
+    # a subset of stages, a row block, too small a frame buffer
+    sub = _lib.DEBUG_PRIMARY_DEPTH | _lib.DEBUG_OCCLUDED_EMISSIVE
+    orc.set_option(_lib.OPT_FIX_Q4, 0)
+    cu.set_option(_lib.OPT_FIX_Q4, 0)
+    want = orc.trace_debug(T.make_block_request(w, h, block_y=16, block_h=32, spp=1, num_bounces=2), seeds, sub)
+    got = cu.trace_debug(T.make_block_request(w, h, block_y=16, block_h=32, spp=1, num_bounces=2), seeds, sub)
+    assert [(f, b) for f, b, _ in got] == [(2, 0), (32, 0), (32, 1)]
+    _assert_frames_close(got, want, key + " row block")
+    import ctypes
+    from polaris_b200._lib import Stats
+    req = T.make_block_request(w, h, spp=1, num_bounces=2)
+    one = np.zeros((1, h, w, 4), np.uint8)
+    info = np.zeros(1, _lib.DEBUG_FRAME_DTYPE)
+    n = ctypes.c_uint32(0)
+    rc = cu._lib.pc_trace_debug(cu._h, ctypes.byref(req), seeds.ctypes.data, seeds.size, sub, one.ctypes.data, one.nbytes, info.ctypes.data, 1,
+                                ctypes.byref(n), ctypes.byref(Stats()))
+    assert rc == _lib.ERR_INVALID_ARGUMENT and n.value == 1
+    orc.close()
+    cu.close()
+
+
+@pytest.mark.parametrize("key", ["c2", "c4"])
+def test_debug_stages_golden(key):
+    from .golden.make_golden import DEBUG_BOUNCES, SPP
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"debug_{key}.npz"))
+    w, h = GOLDEN_CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    cu = C.cuda_for(sc, w, h)
+    got = cu.trace_debug(T.make_block_request(w, h, spp=SPP, num_bounces=DEBUG_BOUNCES), g["seeds"], _lib.DEBUG_ALL_STAGES)
+    want = [(int(f), int(b), fr) for f, b, fr in zip(g["flags"], g["bounces"], g["frames"])]
+    _assert_frames_close(got, want, f"golden {key}")
+    cu.close()
