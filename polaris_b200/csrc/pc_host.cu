@@ -293,8 +293,8 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         // ShadePrimaryRayMisses / ShadeIndirectRayMisses + ShadeHits (pipeline.go:134-146)
         {
             LaunchTimer lt(tr, PC_K_SHADE);
-            k_shade<COUNT><<<shadeGrid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride,
-                                                            perSample, bounce, req.min_bounces_for_rr, a, tr->optFixQ4);
+            shade_launch(COUNT, shadeGrid, s, tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride, perSample, bounce,
+                         req.min_bounces_for_rr, a, tr->optFixQ4);
         }
         L++;
         if (df & PC_DEBUG_THROUGHPUT) debug_stage(tr, ch, req, *dbg, PC_DEBUG_THROUGHPUT, bounce, a);  // :151-157
@@ -500,18 +500,7 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
     if (occPerSM > 16) occPerSM = 16;
     tr->occGrid = tr->prop.multiProcessorCount * occPerSM;
     int shadePerSM = 0;
-    // the shade tile's staging area exceeds the 48 KB static limit: opt in to the dynamic size for both instances
-    cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
-    cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ShadeShared));
-    {   // ask for just enough shared memory for SHADE_MIN_BLOCKS resident tiles; the rest of the 256 KB stays L1
-        const size_t want = (size_t)SHADE_MIN_BLOCKS * (sizeof(ShadeShared) + 1024);
-        int pct = (int)((want * 100 + tr->prop.sharedMemPerMultiprocessor - 1) / tr->prop.sharedMemPerMultiprocessor);
-        if (pct > 100) pct = 100;
-        cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-    }
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shadePerSM, k_shade<false>, SHADE_BLOCK, sizeof(ShadeShared));
-    if (shadePerSM > SHADE_MIN_BLOCKS) shadePerSM = SHADE_MIN_BLOCKS;
+    shade_configure(tr->prop, &shadePerSM);
     if (shadePerSM < 1) shadePerSM = 1;
     tr->shadeGrid = tr->prop.multiProcessorCount * shadePerSM;
     tr->sc.sceneDiffuseMat = -1;

@@ -110,6 +110,7 @@ __device__ __forceinline__ uint32_t next_unit(uint32_t *head) {
     return __shfl_sync(0xFFFFFFFFu, u, 0);
 }
 
+#ifndef PC_SHADE_TU  // non-template kernels live in the exact-arithmetic translation unit only (pc_host.cu)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords, uint32_t sampleStride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,6 +123,8 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
     if (i < MAX_BOUNCES) ctl->ticket[i] = 0;
     for (size_t k = i; k < statusWords; k += stride) status[k] = 0ull;
 }
+
+#endif  // !PC_SHADE_TU
 
 // ------------------------------------------------------------------------------------------------
 // Persistent per-ray traversal with warp-level refilling.
@@ -720,6 +723,17 @@ struct ShadeShared {
     uint32_t tile, occBase, indBase, nextChunk, activeChunks;
 };
 
+// k_shade is compiled in its own translation unit (pc_shade.cu) so that it can carry its own floating-point flags:
+// traversal, ray generation, merge and tonemap -- everything whose results are compared BIT FOR BIT with the CPU oracle --
+// stay IEEE exact (-fmad=false -prec-div=true -prec-sqrt=true); shading is compared within 1e-4 relative and may use the
+// hardware's 2-ulp division / square root, like the reference's own OpenCL build does for its native_recip / native_sqrt
+// / `/` in these very functions (Makefile: SHADE_FP).  The host side reaches it through these two functions.
+void shade_configure(const cudaDeviceProp &prop, int *blocksPerSM);
+void shade_launch(bool count, int grid, cudaStream_t s, const DScene &sc, const FrameBufs &fb, TraceCtl *ctl, const uint32_t *seeds,
+                  unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce, uint32_t minBouncesForRR, int a, int fixQ4);
+const char *shade_fp_mode();
+
+#ifdef PC_SHADE_TU
 template <bool COUNT>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                       unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
@@ -898,6 +912,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
     if (COUNT) warp_add_stat(ctl, ST_SHADED, shaded);
 }
 
+#endif  // PC_SHADE_TU
+
+#ifndef PC_SHADE_TU
 // ------------------------------------------------------------------------------------------------
 // accumulator.cl:5-19, hdr.cl:5-28
 // ------------------------------------------------------------------------------------------------
@@ -1055,5 +1072,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK) k_debug_packet(DScene sc, const Ra
         warp_add_stat(ctl, ST_INSTANCES, st.instances);
     }
 }
+
+#endif  // !PC_SHADE_TU
 
 }  // namespace pc

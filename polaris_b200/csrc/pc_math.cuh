@@ -24,7 +24,7 @@
 #ifdef PC_INLINE_ALL
 #define PC_HD_NOINLINE __host__ __device__ __forceinline__
 #else
-#define PC_HD_NOINLINE __host__ __device__ __noinline__
+#define PC_HD_NOINLINE static __host__ __device__ __noinline__  // static: one copy per translation unit (pc_host.cu, pc_shade.cu)
 #endif
 #define PC_D __device__ __forceinline__
 #else

@@ -131,3 +131,34 @@ def test_derived_layout_properties():
         assert info["top_depth"] >= 0 and info["mesh_depth"] >= 0 and info["stack_need"] >= 1
         assert info["stack_need"] <= 64  # PC_STACK_SIZE; deeper scenes are refused with PC_ERR_STACK_DEPTH
         emu.close()
+
+
+def test_triangle_pretest_is_conservative():
+    """(PC_TRI_PRETEST, measured slower and off by default, kept as a documented experiment.)
+    pc_device.cuh triTest rejects without the IEEE reciprocal only when the reference's own `u < 0 || u > 1`
+    (intersect.cl:266-269) is certain to reject: check the implication on 4M (a, det) pairs spanning the float32
+    range, including denormals, huge values and the neighbourhood of the decision boundaries."""
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    parts = []
+    for lo, hi in ((-150, 128), (-30, 30), (-10, 10)):
+        a = (rng.choice([-1.0, 1.0], n) * np.exp2(rng.uniform(lo, hi, n))).astype(np.float32)
+        det = (rng.choice([-1.0, 1.0], n) * np.exp2(rng.uniform(max(lo, -17), hi, n))).astype(np.float32)  # |det| >= 1e-5
+        parts.append((a, det))
+    det = (rng.choice([-1.0, 1.0], n) * np.exp2(rng.uniform(-16, 20, n))).astype(np.float32)
+    a = (det.astype(np.float64) * (1.0 + rng.uniform(-3e-5, 3e-5, n))).astype(np.float32)  # u close to 1
+    parts.append((a, det))
+    parts.append(((rng.choice([-1.0, 1.0], n) * np.exp2(rng.uniform(-24, -16, n))).astype(np.float32), det))  # |a| around 2^-20
+    for k, (a, det) in enumerate(parts):
+        keep = np.abs(det) >= np.float32(1e-5)
+        a, det = a[keep], det[keep]
+        with np.errstate(all="ignore"):
+            inv = (np.float32(1.0) / det).astype(np.float32)
+            u = (a * inv).astype(np.float32)
+            ref_reject = (u < 0) | (u > 1)
+            neg = (a < 0) != (det < 0)
+            aa = np.abs(a)
+            pre = np.where(neg, aa >= np.float32(9.5367431640625e-07), aa > (np.abs(det) * np.float32(1.00001)).astype(np.float32))
+        assert not (pre & ~ref_reject).any()
+        if k < 3:
+            assert pre.mean() > 0.3  # and the filter does fire on generic inputs

@@ -3,4 +3,4 @@
 name=$1; shift
 cd "$(dirname "$0")/../polaris_b200/csrc" || exit 1
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
-  -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -shared -o ../../ab_${name}.so pc_host.cu -lcudart 2>&1 | grep -E "error" ; ls -la ../../ab_${name}.so
+  -Xcompiler -fPIC --expt-relaxed-constexpr "$@" -shared -o ../../ab_${name}.so pc_host.cu pc_shade.cu -lcudart 2>&1 | grep -E "error" ; ls -la ../../ab_${name}.so

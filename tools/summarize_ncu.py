@@ -26,7 +26,7 @@ md = [f"# ncu summary {R} (bench.py --steps 1 --warmup 1 --spp 4 --chains 1, con
       "`--set full --clock-control none --import-source on`, two launches per kernel class (skip 6).  Durations under ncu are",
       "cold-cache and serialised: compare shares, not absolutes.  dram bytes are per launch.\n"]
 traffic = {}
-for k in ("k_shade", "k_query", "k_occlusion", "k_primary"):
+for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
     rep = os.path.join(G, f"prof_{k}_{R}.ncu-rep")
     if not os.path.exists(rep):
         continue
