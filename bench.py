@@ -152,8 +152,9 @@ def cpu_trace_sample(sc, w, h, spp, config_number, rows=None):
     tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
     tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
-    bh = rows or h
-    req = T.make_block_request(w, h, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+    bh = min(rows or h, h)
+    by = (h - bh) // 2  # a bounded sample takes the MIDDLE rows of the frame: the top rows of the terrain frame are sky only
+    req = T.make_block_request(w, h, block_y=by, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
     seeds = T.splitmix_seeds(config_number, spp * (1 + NUM_BOUNCES))
     t0 = time.perf_counter()
     tr.trace(req, seeds)
@@ -182,11 +183,12 @@ def opencl_reference_sample(sc, w, h, spp, config_number, rows=None):
         tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
         tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
         tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
-        bh = rows or h
+        bh = min(rows or h, h)
+        by = (h - bh) // 2  # middle rows, like the CPU sample
         seeds = T.splitmix_seeds(config_number, spp * (1 + NUM_BOUNCES))
         best = None
         for _ in range(2):  # first pass warms the driver's lazily built kernels
-            req = T.make_block_request(w, h, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+            req = T.make_block_request(w, h, block_y=by, block_h=bh, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
             t0 = time.perf_counter()
             tr.trace(req, seeds)
             tr.merge_output(tr, req)
@@ -200,7 +202,7 @@ def opencl_reference_sample(sc, w, h, spp, config_number, rows=None):
         tr.close()
         return {"value": best[0] / 1e6, "unit": "Mrays/s", "kind": "reference OpenCL kernels + launch discipline (clFinish per launch), same GPU",
                 "device": desc["device"], "platform": desc["platform_version"], "launches": int(best[3]),
-                "sample": f"{w}x{bh} rows of the {w}x{h} frame, {spp} spp ({best[2]} rays in {best[1]:.3f}s, best of 2)"}
+                "sample": f"rows {by}..{by + bh} of the {w}x{h} frame, {spp} spp ({best[2]} rays in {best[1]:.3f}s, best of 2)"}
     except Exception as e:  # a baseline must never take the bench down
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
@@ -228,7 +230,7 @@ def run_reference(args):
             vals.append(v)
             times.append(dt)
     value = float(np.mean(vals))
-    sample = f"{w}x{rows} rows of the {w}x{h} frame, {spp} spp of {spp_full} per step"
+    sample = f"the middle {rows} rows of the {w}x{h} frame, {spp} spp of {spp_full} per step"
     line = {
         "impl": "reference", "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3), "higher_is_better": True,
@@ -388,7 +390,7 @@ def run_cuda_single(args):
         cpu_rows = h if w * h <= 1024 * 1024 else max(16, (1024 * 1024) // w)  # bound the sample on the big frames
         v, cores, kind, cdt, crays = cpu_trace_sample(sc, w, h, args.cpu_spp, cfgno, cpu_rows)
         cpu = {"value": v, "unit": "Mrays/s", "cores": cores, "kind": kind,
-               "sample": f"{w}x{cpu_rows} rows of the {w}x{h} frame, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
+               "sample": f"the middle {cpu_rows} rows of the {w}x{h} frame, {args.cpu_spp} spp of {spp} ({crays} rays in {cdt:.1f}s)"}
         log(f"[bench] cpu baseline ({kind}, {cores} cores): {v:.2f} Mrays/s")
     ocl = None
     if not args.no_cpu and not args.no_opencl:
