@@ -110,6 +110,34 @@ __device__ __forceinline__ uint32_t next_unit(uint32_t *head) {
     return __shfl_sync(0xFFFFFFFFu, u, 0);
 }
 
+// Units that shrink when the queue runs dry (PC_ADAPTIVE_UNITS, OFF).  Idea: a launch ends with a tail in which a few
+// warps each serialise the divergent walks of a 32-ray unit, so once fewer than 32 rays per resident warp are left,
+// smaller units (and smaller k_shade tiles) would spread the same rays over more warps.  MEASURED AND REJECTED
+// (profiles/ab_r01i.txt): -9 % on config 2 (3 860 -> 3 512 Mrays/s), -27 % on config 1, -6 % on config 3, -3 % on the 4K
+// frame, -2 % even with a single sample chain: the tail is not idle -- the other chains' kernels run in it -- and the
+// extra warp instructions of the small units cost more than the shorter tail saves.  Kept for the record.
+#ifndef PC_ADAPTIVE_UNITS
+#define PC_ADAPTIVE_UNITS 0
+#endif
+struct UnitClaim {
+    uint32_t seen;  // queue position after this warp's last claim (0 before the first)
+};
+__device__ __forceinline__ uint32_t next_unit_adaptive(uint32_t *head, uint32_t n, UnitClaim &c, uint32_t &size) {
+    uint32_t u = 0, sz = 32u;
+    if (lane_id() == 0) {
+#if PC_ADAPTIVE_UNITS
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        const uint32_t left = n > c.seen ? n - c.seen : 0u;
+        sz = left >= 32u * warps ? 32u : left >= 16u * warps ? 16u : left >= 8u * warps ? 8u : 4u;
+#endif
+        u = atomicAdd(head, sz);
+    }
+    size = __shfl_sync(0xFFFFFFFFu, sz, 0);
+    u = __shfl_sync(0xFFFFFFFFu, u, 0);
+    c.seen = u + size;
+    return u;
+}
+
 #ifndef PC_SHADE_TU  // non-template kernels live in the exact-arithmetic translation unit only (pc_host.cu)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords, uint32_t sampleStride) {
@@ -170,11 +198,13 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
 // Fixed units: a warp pulls 32 consecutive rays and every lane walks its ray with traverse().
 template <bool ANY_HIT, bool COUNT, class Source, class Sink>
 __device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink) {
+    UnitClaim claim{0u};
     for (;;) {
-        const uint32_t unit = next_unit(head);
+        uint32_t size;
+        const uint32_t unit = next_unit_adaptive(head, n, claim, size);
         if (unit >= n) break;
         const uint32_t i = unit + lane_id();
-        if (i < n) {
+        if (lane_id() < size && i < n) {
             float3 o, d;
             float tmax;
             src.load(i, o, d, tmax);
@@ -575,48 +605,50 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
 // query of the indirect rays (rays[a]) and the any-hit test of the occlusion rays (rays[2]) with its
 // emissive accumulation.  Neither reads what the other writes (hits / hit flags vs. the trace
 // accumulator), the reference only runs them back to back because its host loop is serial
-// (pipeline.go:160-165 then :203-209).  One queue covers both: the first ceil32(nQuery) items are
-// query units (the longer walks first, so the launch's tail is made of the cheap any-hit rays),
-// the rest occlusion units.  Saves one launch tail per bounce.
+// (pipeline.go:160-165 then :203-209).  Two queue heads: every warp drains the closest-hit queue first (the
+// longer walks), then the any-hit queue, whose cheap rays make the launch's tail.  Saves one launch tail per bounce.
 template <bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot) {
     const uint32_t nQ = (uint32_t)ctl->numRays[a], nO = (uint32_t)ctl->numRays[2];
-    const uint32_t unitsQ = (nQ + 31u) & ~31u;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)nQ);
         atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
     }
     TravStats st{0, 0, 0};
     uint32_t missed = 0, unocc = 0;
-    uint32_t *head = &ctl->queueHead[queueSlot];
     const Ray *qrays = fb.rays[a], *orays = fb.rays[2];
-    for (;;) {
-        const uint32_t unit = next_unit(head);
-        if (unit >= unitsQ + nO) break;
-        if (unit < unitsQ) {
-            const uint32_t i = unit + lane_id();
-            if (i < nQ) {
-                const Ray r = ld_ray(qrays + i);
-                Hit best;
-                const int hit = traverse<false, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
-                __stcs(fb.hitFlags + i, (uint32_t)hit);
-                st_hit(fb.hits + i, best.wuvt, best.inst, best.tri);
-                if (COUNT && !hit) missed++;
-            }
-        } else {
-            const uint32_t i = unit - unitsQ + lane_id();
-            if (i < nO) {
-                const Ray r = ld_ray(orays + i);
-                Hit best;
-                const int hit = traverse<true, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
-                if (!hit) {
-                    const uint32_t pixel = fb.paths[(uint32_t)r.dir.w].meta.x;  // rayGetPathIndex (util/ray.cl:26-28)
-                    const float4 s = __ldcs(fb.emissiveSamples + i);
-                    float4 c = fb.traceAcc[pixel];
-                    c.x += s.x; c.y += s.y; c.z += s.z;
-                    fb.traceAcc[pixel] = c;
-                    if (COUNT) unocc++;
-                }
+    UnitClaim claim{0u};
+    for (;;) {  // the closest-hit queue first ...
+        uint32_t size;
+        const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot], nQ + nO, claim, size);
+        if (unit >= nQ) break;
+        const uint32_t i = unit + lane_id();
+        if (lane_id() < size && i < nQ) {
+            const Ray r = ld_ray(qrays + i);
+            Hit best;
+            const int hit = traverse<false, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+            __stcs(fb.hitFlags + i, (uint32_t)hit);
+            st_hit(fb.hits + i, best.wuvt, best.inst, best.tri);
+            if (COUNT && !hit) missed++;
+        }
+    }
+    claim.seen = 0u;
+    for (;;) {  // ... then the any-hit queue, whose short walks make the launch's tail
+        uint32_t size;
+        const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot + 1], nO, claim, size);
+        if (unit >= nO) break;
+        const uint32_t i = unit + lane_id();
+        if (lane_id() < size && i < nO) {
+            const Ray r = ld_ray(orays + i);
+            Hit best;
+            const int hit = traverse<true, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+            if (!hit) {
+                const uint32_t pixel = fb.paths[(uint32_t)r.dir.w].meta.x;  // rayGetPathIndex (util/ray.cl:26-28)
+                const float4 s = __ldcs(fb.emissiveSamples + i);
+                float4 c = fb.traceAcc[pixel];
+                c.x += s.x; c.y += s.y; c.z += s.z;
+                fb.traceAcc[pixel] = c;
+                if (COUNT) unocc++;
             }
         }
     }
@@ -744,7 +776,16 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned ltMask = (1u << lane) - 1u;
     const uint32_t n = (uint32_t)ctl->numRays[a];
-    const uint32_t nTiles = (n + SHADE_TILE - 1u) / SHADE_TILE;
+    // (PC_ADAPTIVE_UNITS, off: measured slower, see next_unit_adaptive) tile size follows the launch: the largest tile that
+    // still gives every CTA at least two tiles
+#if PC_ADAPTIVE_UNITS
+    uint32_t rpt = SHADE_RPT;
+    while (rpt > 1u && n < 2u * gridDim.x * rpt * SHADE_BLOCK) rpt >>= 1;
+#else
+    const uint32_t rpt = SHADE_RPT;
+#endif
+    const uint32_t tileRays = rpt * SHADE_BLOCK;
+    const uint32_t nTiles = (n + tileRays - 1u) / tileRays;
     if (n == 0 && blockIdx.x == 0 && tid == 0) {  // resources.go:230-238: both counters reset
         ctl->numRays[2] = 0;
         ctl->numRays[1 - a] = 0;
@@ -758,13 +799,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= nTiles) break;
-        const uint32_t base = tile * SHADE_TILE;
+        const uint32_t base = tile * tileRays;
         // ---- 1. sort keys of my SHADE_RPT rays (slot = r * SHADE_BLOCK + tid: coalesced), counted per key.
         //         Which thread later shades which ray does not matter (results are staged at the ray's slot),
         //         so the position inside a key's range is simply the order of arrival.
         uint32_t key[SHADE_RPT], rank[SHADE_RPT];
 #pragma unroll
         for (int r = 0; r < SHADE_RPT; r++) {
+            if ((uint32_t)r >= rpt) break;
             const uint32_t slot = r * SHADE_BLOCK + tid, i = base + slot;
             uint32_t k = KEY_INACTIVE, tri = 0xFFFFFFFFu;
             if (i < n) {
@@ -800,7 +842,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < SHADE_RPT; r++) sh.perm[sh.hist[key[r]] + rank[r]] = (uint16_t)(r * SHADE_BLOCK + tid);
+        for (int r = 0; r < SHADE_RPT; r++)
+            if ((uint32_t)r < rpt) sh.perm[sh.hist[key[r]] + rank[r]] = (uint16_t)(r * SHADE_BLOCK + tid);
         __syncthreads();
         // ---- 2. warps pull 32-ray chunks of the sorted tile
         const uint32_t activeChunks = sh.activeChunks;
@@ -860,6 +903,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         unsigned occMask[SHADE_RPT], indMask[SHADE_RPT];
 #pragma unroll
         for (int r = 0; r < SHADE_RPT; r++) {
+            if ((uint32_t)r >= rpt) break;
             const uint32_t g = r * SHADE_WARPS + warp;
             const uint32_t f = sh.flags[g * 32u + lane];
             occMask[r] = __ballot_sync(FULL, (f & 1u) != 0u);
@@ -868,14 +912,15 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         }
         __syncthreads();
         if (warp == 0) {
-            const uint32_t o = lane < SHADE_GROUPS ? sh.groupOcc[lane] : 0u, q = lane < SHADE_GROUPS ? sh.groupInd[lane] : 0u;
+            const uint32_t groups = rpt * SHADE_WARPS;
+            const uint32_t o = lane < groups ? sh.groupOcc[lane] : 0u, q = lane < groups ? sh.groupInd[lane] : 0u;
             uint32_t io = o, iq = q;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t uo = __shfl_up_sync(FULL, io, d), uq = __shfl_up_sync(FULL, iq, d);
                 if ((int)lane >= d) { io += uo; iq += uq; }
             }
-            if (lane < SHADE_GROUPS) { sh.groupOcc[lane] = io - o; sh.groupInd[lane] = iq - q; }
+            if (lane < groups) { sh.groupOcc[lane] = io - o; sh.groupInd[lane] = iq - q; }
             const uint32_t occTot = __shfl_sync(FULL, io, 31), indTot = __shfl_sync(FULL, iq, 31);
             uint32_t occBase, indBase;
             lookback(status, tile, occTot, indTot, occBase, indBase);
@@ -894,6 +939,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < SHADE_RPT; r++) {
+            if ((uint32_t)r >= rpt) break;
             const uint32_t g = r * SHADE_WARPS + warp, slot = g * 32u + lane;
             const float pif = sh.pathIndexF[slot];
             if (occMask[r] & (1u << lane)) {  // pt_integrator.cl:200-204
