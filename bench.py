@@ -423,7 +423,7 @@ def run_cuda_multi(args):
     import torch.distributed as dist
 
     from polaris_b200 import tracer as T
-    from polaris_b200.gather import gather_rows_to_primary
+    from polaris_b200.gather import RowGather, StatsExchange
     from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -446,12 +446,48 @@ def run_cuda_multi(args):
     sched = PerfectScheduler()
     speeds = [StaticSpeed(tr.speed()) for _ in range(world)]
     seeds = T.splitmix_seeds(cfgno + 100 * rank, pass_spp * (1 + NUM_BOUNCES))
-    recv = torch.empty(w * h * 4, dtype=torch.float32, device="cuda") if rank == 0 else None
+    recv_bufs = [torch.empty(w * h * 4, dtype=torch.float32, device="cuda") if rank == 0 else None for _ in range(2)]
     acc_samples = 0
+    # The exchange is split phase (polaris_b200/gather.py): pass i's rows travel to rank 0, are added and tonemapped while
+    # pass i+1 is being traced; the scheduler's feedback is read two passes late (it was posted a whole pass earlier, so
+    # reading it never waits for a slower rank).  drain() completes everything in flight: the timed region ends with it.
+    pending_gather = []   # at most one: (RowGather, rows, acc_samples of that pass, e2e)
+    pending_stats = []    # StatsExchange objects, oldest first
+    totals = {"rays": 0.0, "launches": 0.0, "have_stats": False}
+
+    def read_stats(keep):
+        while len(pending_stats) > keep:
+            res = pending_stats.pop(0).result()
+            totals["have_stats"] = True
+            for r in range(world):
+                speeds[r].set_stats(int(res[r][0]), float(res[r][1]))
+            totals["rays"] += sum(x[2] for x in res)
+            totals["launches"] += sum(x[3] for x in res)
+            if rank == 0 and args.verbose:
+                log(f"[bench] pass: rows {[int(x[0]) for x in res]} trace ms {[round(x[1] * 1e3, 1) for x in res]}")
+
+    def finish_gather():
+        if not pending_gather:
+            return
+        rg, rows, acc0, e2e = pending_gather.pop(0)
+        blocks = rg.finish()
+        if rank == 0:
+            torch.cuda.current_stream().synchronize()  # the received rows are complete before pc_merge_rows reads them on its own stream
+            for r in range(1, world):
+                rr = T.make_block_request(w, h, block_y=int(sum(rows[:r])), block_h=int(rows[r]), spp=pass_spp,
+                                          accumulated_samples=acc0 + pass_spp)
+                tr.merge_rows(blocks[r].data_ptr(), True, rr)
+            tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc0), want_pixels=e2e)
+
+    def drain():
+        finish_gather()
+        read_stats(0)
 
     def step(e2e=False):
         nonlocal acc_samples
-        rows = sched.schedule(speeds, h)  # identical on every rank: fed by all-gathered timings below
+        # feedback for the perfect scheduler (scheduler.go:50-80), posted a whole pass ago (the very first one is waited for)
+        read_stats(1 if totals["have_stats"] else 0)
+        rows = sched.schedule(speeds, h)  # identical on every rank: fed by the all-gathered timings
         by = int(sum(rows[:rank]))
         req = T.make_block_request(w, h, block_y=by, block_h=int(rows[rank]), spp=pass_spp, num_bounces=NUM_BOUNCES,
                                    min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=acc_samples)
@@ -462,63 +498,70 @@ def run_cuda_multi(args):
         tr.trace(req, seeds)
         t_trace = time.perf_counter() - t0
         d = tr.stats().device
-        t1 = time.perf_counter()
-        # exchange step: block rows -> rank 0 over NCCL (NVLink), added into the frame accumulator
+        finish_gather()  # the previous pass's rows arrived while this one was traced: add + tonemap on rank 0
+        # exchange step of THIS pass: block rows -> rank 0 over NCCL (NVLink); rank 0's own rows go straight into its frame accumulator
         ptr, nbytes = tr.trace_rows(req)
         mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
-        blocks = gather_rows_to_primary(mine, rows, w, rank, world, recv)
         if rank == 0:
             tr.merge_output(tr, req)
-            torch.cuda.synchronize()  # the received rows are complete before pc_merge_rows reads them on its own stream
-            for r in range(1, world):
-                rr = T.make_block_request(w, h, block_y=int(sum(rows[:r])), block_h=int(rows[r]), spp=pass_spp,
-                                          accumulated_samples=acc_samples + pass_spp)
-                tr.merge_rows(blocks[r].data_ptr(), True, rr)
-            tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc_samples), want_pixels=e2e)
-        t2 = time.perf_counter()
-        # feedback for the perfect scheduler (scheduler.go:50-80): rows and render time of every tracer
-        t = torch.tensor([float(rows[rank]), t_trace, float(d["query_rays"] + d["occlusion_rays"]), float(d["kernel_launches"])],
-                         dtype=torch.float64, device="cuda")
-        allt = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allt, t)
-        for r in range(world):
-            speeds[r].set_stats(int(allt[r][0].item()), float(allt[r][1].item()))
+        pending_gather.append((RowGather(rows, w, rank, world).start(mine, recv_bufs[(acc_samples // pass_spp) % 2]), rows, acc_samples, e2e))
+        pending_stats.append(StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"]], world, "cuda"))
         acc_samples += pass_spp
-        if rank == 0 and args.verbose:
-            log(f"[bench] step: rows {[int(x[0].item()) for x in allt]} trace ms {[round(x[1].item() * 1e3, 1) for x in allt]} "
-                f"device ms(rank0) {d['device_time_ns'] / 1e6:.1f} gather+merge+tonemap {1e3 * (t2 - t1):.1f} ms, stats exchange {1e3 * (time.perf_counter() - t2):.1f} ms")
-        return sum(float(x[2].item()) for x in allt), sum(float(x[3].item()) for x in allt)
 
+    # the SAME workload on ONE of these GPUs (rank 0 traces the whole frame, the others wait): the N = 1 default of this
+    # script is configs[1], a different frame, so the 1-GPU point of the configs[4] scaling curve is measured here
+    one_gpu = None
+    if not args.no_single:
+        if rank == 0:
+            vals = []
+            for i in range(3):
+                req1 = T.make_block_request(w, h, spp=pass_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tr.trace(req1, seeds)
+                tr.merge_output(tr, req1)
+                tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE), want_pixels=False)
+                torch.cuda.synchronize()
+                d1 = tr.stats().device
+                if i:
+                    vals.append((d1["query_rays"] + d1["occlusion_rays"]) / (time.perf_counter() - t0) / 1e6)
+            one_gpu = {"value": float(np.mean(vals)), "unit": "Mrays/s", "passes": len(vals),
+                       "note": "one 64-spp pass of the whole frame on rank 0's GPU alone, same scene / seeds / kernels, measured in this run"}
+            log(f"[bench] the same workload on one GPU: {one_gpu['value']:.1f} Mrays/s")
+        dist.barrier()
     for i in range(args.warmup):
         step()
+    drain()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     dist.barrier()
     torch.cuda.synchronize()
+    totals["rays"] = totals["launches"] = 0.0
     t0 = time.perf_counter()
-    rays = launches = 0.0
     for _ in range(args.steps):
-        r, l = step()
-        rays += r
-        launches += l
+        step()
+    drain()  # the last pass's rows are gathered, added and tonemapped inside the timed region
     dist.barrier()
     torch.cuda.synchronize()
+    rays, launches = totals["rays"], totals["launches"]
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
     clk = clocks.stop() if rank == 0 else None
     # e2e
     step(e2e=True)
+    drain()
     dist.barrier()
     torch.cuda.synchronize()
+    totals["rays"] = 0.0
     t0 = time.perf_counter()
-    e_rays = 0.0
     for _ in range(args.steps):
-        r, _ = step(e2e=True)
-        e_rays += r
+        step(e2e=True)
+    drain()
     dist.barrier()
     torch.cuda.synchronize()
+    e_rays = totals["rays"]
     e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e_dt = float(e_dt.item())
@@ -531,7 +574,7 @@ def run_cuda_multi(args):
             "clocks": clk, "rows_last_step": [int(s.block_h) for s in speeds],
             "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s",
                     "h2d_bytes_per_step": int((sc.nbytes() + seeds.nbytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": None, "cpu_baseline": None, "one_gpu_same_workload": one_gpu,
         }
         emit(line)
     tr.close()
@@ -567,6 +610,7 @@ def main():
     ap.add_argument("--spp", type=int, default=0, help="override samples per step (debugging only; invalidates the config)")
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single", action="store_true", help="N > 1: skip the one-GPU measurement of the same workload")
     ap.add_argument("--no-opencl", action="store_true", help="skip the reference-OpenCL-kernels-on-this-GPU baseline")
     ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
     ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")

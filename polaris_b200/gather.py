@@ -16,30 +16,74 @@ import torch
 import torch.distributed as dist
 
 
+class RowGather:
+    """One exchange in flight.  Split phase so that the next pass can be traced while the rows travel: `start` snapshots
+    this rank's block rows (the tracer clears its accumulator at the start of the next `Trace`, tracer.go:215) and posts
+    the sends / receives, `finish` waits and hands rank 0 the per-rank row tensors."""
+
+    def __init__(self, rows, frame_w: int, rank: int, world: int):
+        self.rows = [int(r) for r in rows]
+        self.frame_w, self.rank, self.world = frame_w, rank, world
+        self.works, self.blocks, self._keep = [], None, None
+
+    def start(self, mine: torch.Tensor, recv: torch.Tensor | None = None, snapshot: bool = True):
+        rows, w, rank, world = self.rows, self.frame_w, self.rank, self.world
+        assert mine.numel() == rows[rank] * w * 4, (mine.numel(), rows[rank], w)
+        mine = mine.reshape(-1)
+        if snapshot and (world > 1 and rank != 0):
+            mine = mine.clone()  # 16 B/px of the block, device to device
+        self._keep = mine
+        if world == 1:
+            self.blocks = [mine.reshape(rows[0], w, 4)]
+            return self
+        if rank != 0:
+            self.works.append(dist.isend(mine.contiguous(), dst=0))
+            return self
+        need = sum(rows[1:]) * w * 4
+        if recv is None or recv.numel() < need:
+            recv = torch.empty(need, dtype=torch.float32, device=mine.device)
+        self._keep = (mine, recv)
+        out, off = [mine.reshape(rows[0], w, 4)], 0
+        for r in range(1, world):
+            n = rows[r] * w * 4
+            view = recv[off:off + n]
+            self.works.append(dist.irecv(view, src=r))
+            out.append(view.reshape(rows[r], w, 4))
+            off += n
+        self.blocks = out
+        return self
+
+    def finish(self):
+        for wk in self.works:
+            wk.wait()
+        self.works = []
+        return self.blocks if self.rank == 0 else None
+
+
 def gather_rows_to_primary(mine: torch.Tensor, rows, frame_w: int, rank: int, world: int, recv: torch.Tensor | None = None):
     """`mine`: this rank's block rows, float32, rows[rank]*frame_w*4 elements (any shape).
     Returns on rank 0 the list of per-rank row tensors shaped (rows[r], frame_w, 4) (entry 0 is `mine`),
     on every other rank None.  `recv` is an optional reusable flat receive buffer on rank 0."""
-    rows = [int(r) for r in rows]
-    assert mine.numel() == rows[rank] * frame_w * 4, (mine.numel(), rows[rank], frame_w)
-    if world == 1:
-        return [mine.reshape(rows[0], frame_w, 4)]
-    if rank != 0:
-        dist.send(mine.reshape(-1).contiguous(), dst=0)
-        return None
-    need = sum(rows[1:]) * frame_w * 4
-    if recv is None or recv.numel() < need:
-        recv = torch.empty(need, dtype=torch.float32, device=mine.device)
-    out, works, off = [mine.reshape(rows[0], frame_w, 4)], [], 0
-    for r in range(1, world):
-        n = rows[r] * frame_w * 4
-        view = recv[off:off + n]
-        works.append(dist.irecv(view, src=r))
-        out.append(view.reshape(rows[r], frame_w, 4))
-        off += n
-    for wk in works:
-        wk.wait()
-    return out
+    return RowGather(rows, frame_w, rank, world).start(mine, recv, snapshot=False).finish()
+
+
+class StatsExchange:
+    """`exchange_stats`, split phase: post the all-gather, read it a pass later (the scheduler then works from timings that
+    are one pass old, which changes nothing once the assignment has converged)."""
+
+    def __init__(self, values, world: int, device="cpu"):
+        self.world = world
+        self.t = torch.tensor([float(x) for x in values], dtype=torch.float64, device=device)
+        self.all = [torch.zeros_like(self.t) for _ in range(world)]
+        self.work = dist.all_gather(self.all, self.t, async_op=True) if world > 1 else None
+        if world == 1:
+            self.all = [self.t]
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        return [a.tolist() for a in self.all]
 
 
 def exchange_stats(block_h: int, render_time_s: float, rank: int, world: int, device="cpu", extra=()):

@@ -24,13 +24,13 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, split_phase=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from polaris_b200 import _lib
     from polaris_b200 import tracer as T
-    from polaris_b200.gather import gather_rows_to_primary, exchange_stats
+    from polaris_b200.gather import RowGather, StatsExchange, exchange_stats, gather_rows_to_primary
     from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
     from tests import common as C
 
@@ -48,9 +48,17 @@ def _worker(rank, world, port, out_path):
         seeds = T.splitmix_seeds(100 + 10 * p + rank, spp * 6)
         tr.trace(req, seeds)
         mine = tr.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).reshape(h, w, 4)[by:by + rows[rank]].copy()
-        blocks = gather_rows_to_primary(torch.from_numpy(mine), rows, w, rank, world)
-        # fake, deterministic render times so both ranks compute the same next assignment
-        stats = exchange_stats(rows[rank], 0.001 * (1 + 3 * rank), rank, world)
+        if split_phase:  # what bench.py does: post the exchange, trace on, collect later (here: at once, after clobbering `mine`)
+            rg = RowGather(rows, w, rank, world).start(torch.from_numpy(mine))
+            se = StatsExchange([rows[rank], 0.001 * (1 + 3 * rank)], world)
+            if rank != 0:
+                mine[:] = -1.0  # the tracer clears its accumulator at the next Trace: the snapshot must already be taken
+            blocks = rg.finish()
+            stats = [(int(a[0]), a[1]) for a in se.result()]
+        else:
+            blocks = gather_rows_to_primary(torch.from_numpy(mine), rows, w, rank, world)
+            # fake, deterministic render times so both ranks compute the same next assignment
+            stats = exchange_stats(rows[rank], 0.001 * (1 + 3 * rank), rank, world)
         for r in range(world):
             speeds[r].set_stats(*stats[r])
         history.append(rows)
@@ -64,7 +72,8 @@ def _worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
-def test_row_gather_world2(tmp_path):
+@pytest.mark.parametrize("split_phase", [False, True])
+def test_row_gather_world2(tmp_path, split_phase):
     sys.path.insert(0, ROOT)
     from polaris_b200 import _lib
     from polaris_b200 import tracer as T
@@ -72,7 +81,7 @@ def test_row_gather_world2(tmp_path):
 
     out = str(tmp_path / "gather")
     port = _free_port()
-    mp.start_processes(_worker, args=(2, port, out), nprocs=2, join=True, start_method="spawn")
+    mp.start_processes(_worker, args=(2, port, out, split_phase), nprocs=2, join=True, start_method="spawn")
     rows = np.load(out + ".rows.npy")
     w, h, spp = 64, 48, 1
     assert rows.shape == (2, 2) and rows[0].tolist() == [24, 24] and rows.sum(axis=1).tolist() == [h, h]
