@@ -30,7 +30,13 @@
 namespace pc {
 
 constexpr int MAX_BOUNCES = 32;
-constexpr int TRAV_BLOCK = 128;   // 4 warps
+#ifndef PC_TRAV_BLOCK
+#define PC_TRAV_BLOCK 128   // 4 warps
+#endif
+constexpr int TRAV_BLOCK = PC_TRAV_BLOCK;
+#ifndef PC_PRIMARY_MIN_BLOCKS
+#define PC_PRIMARY_MIN_BLOCKS 8   // 64 registers: +1 % on configs 3 and 4 over 6 blocks at 80 registers (profiles/ab_r01j.txt)
+#endif
 #ifndef PC_SHADE_BLOCK
 #define PC_SHADE_BLOCK 256
 #endif
@@ -436,7 +442,7 @@ struct PrimarySource {
 
 // MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray
 template <int MODE, bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK) k_primary(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                        const TraceParams *params, uint32_t seedsPerSample, int queueSlot) {
     __shared__ uint2 s_stack[MODE == 1 ? (TRAV_BLOCK / 32) * PC_STACK_SIZE : 1];
     const CameraParams cam = params->cam;
