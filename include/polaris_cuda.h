@@ -143,9 +143,13 @@ typedef enum pc_option {
                                    > 0 accumulate separately and are added in chain order at the
                                    end of pc_trace (deterministic; differs from 1 chain only in
                                    float summation order)                                   */
-    PC_OPT_FUSE_TRACE = 7       /* 1: a bounce's occlusion test (+ emissive accumulation) and the
+    PC_OPT_FUSE_TRACE = 7,      /* 1: a bounce's occlusion test (+ emissive accumulation) and the
                                    next bounce's closest-hit query run as ONE persistent launch;
                                    results are bit-identical to 0 (two launches)              */
+    PC_OPT_SORT_RAYS = 8        /* 1: k_shade also writes, per tile, a permutation of the emitted occlusion /
+                                   indirect rays sorted by (origin octant of the scene, direction octant,
+                                   dominant axis) and the traversal kernels walk the rays in that order;
+                                   the rays, their order in the buffers and every result stay bit-identical */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */

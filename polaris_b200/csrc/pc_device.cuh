@@ -31,6 +31,8 @@ struct DScene {
     const uint8_t *texData;
     uint32_t numEmissives;
     int32_t sceneDiffuseMat;
+    // world bounds (top-level BVH root box) as origin-cell transform of the traversal-order sort key: cell = (o - min) * scale
+    float3 worldMin, worldCellScale;
 };
 
 constexpr uint32_t REF_LEAF = 0x80000000u;

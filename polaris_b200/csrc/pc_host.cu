@@ -21,6 +21,9 @@
 #include "../../include/polaris_cuda.h"
 #include "pc_kernels.cuh"
 
+#ifndef PC_DEFAULT_SORT_RAYS
+#define PC_DEFAULT_SORT_RAYS 1
+#endif
 #ifndef PC_DEFAULT_FUSE_TRACE
 #define PC_DEFAULT_FUSE_TRACE 1
 #endif
@@ -54,19 +57,19 @@ struct DevBuf {
 // boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
     uint32_t nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0;
     uint64_t sceneEpoch = 0;
     const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
         return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
-               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sceneEpoch == o.sceneEpoch && seedsPtr == o.seedsPtr;
+               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && sceneEpoch == o.sceneEpoch && seedsPtr == o.seedsPtr;
     }
 };
 
 constexpr int MAX_CHAINS = 8;
 constexpr int GRAPH_SAMPLES_PER_CHAIN = 4;  // samples each chain contributes to one replay of the captured graph
 struct Chain {
-    DevBuf rays[3], paths, hitFlags, hits, emSamples, ctl, status, acc;  // acc: chains > 0 only
+    DevBuf rays[3], paths, hitFlags, hits, emSamples, ctl, status, acc, permOcc, permInd;  // acc: chains > 0 only
     FrameBufs fb{};
     cudaStream_t stream = nullptr;  // chain 0 uses the handle's stream
     cudaEvent_t evJoin = nullptr;
@@ -103,7 +106,7 @@ struct pc_tracer {
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS;
     int occGrid = 0;
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
@@ -286,6 +289,7 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     L++;
     slot++;
     int a = 0;
+    const int sorted = tr->optSort && !tr->optRefOrder ? 1 : 0;  // traversal order of the bounce rays (k_shade writes the permutations)
     const uint32_t df = dbg ? dbg->flags : 0u;
     if (df & PC_DEBUG_PRIMARY_DEPTH) debug_stage(tr, ch, req, *dbg, PC_DEBUG_PRIMARY_DEPTH, 0, a);      // pipeline.go:113-119
     if (df & PC_DEBUG_PRIMARY_NORMALS) debug_stage(tr, ch, req, *dbg, PC_DEBUG_PRIMARY_NORMALS, 0, a);  // :120-126
@@ -294,7 +298,7 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         {
             LaunchTimer lt(tr, PC_K_SHADE);
             shade_launch(COUNT, shadeGrid, s, tr->sc, fb, ctl, seeds, status + (size_t)bounce * tr->statusStride, perSample, bounce,
-                         req.min_bounces_for_rr, a, tr->optFixQ4);
+                         req.min_bounces_for_rr, a, tr->optFixQ4, sorted);
         }
         L++;
         if (df & PC_DEBUG_THROUGHPUT) debug_stage(tr, ch, req, *dbg, PC_DEBUG_THROUGHPUT, bounce, a);  // :151-157
@@ -303,7 +307,7 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
             // (pipeline.go:160-165, :203-209) are independent: one persistent launch covers both
             a = 1 - a;
             LaunchTimer lt(tr, PC_K_TRACE);
-            k_trace<COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot);
+            k_trace<COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot, sorted);
             L++;
             slot += 2;
             continue;
@@ -312,9 +316,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
         if (tr->optRefOrder)
-            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot);
+            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
         else
-            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot);
+            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
         }
         L++;
         slot++;
@@ -326,9 +330,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
             a = 1 - a;
             LaunchTimer lt(tr, PC_K_QUERY);
             if (tr->optRefOrder)
-                k_query<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot);
+                k_query<true, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot, nullptr);
             else
-                k_query<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot);
+                k_query<false, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[a], fb.hitFlags, fb.hits, ctl, a, slot, sorted ? fb.permInd : nullptr);
             L++;
             slot++;
         }
@@ -378,6 +382,8 @@ int ensure_chains(pc_tracer *tr, int want) {
         CU(tr, PC_ERR_ALLOC, ch.hitFlags.alloc(px * 4));
         CU(tr, PC_ERR_ALLOC, ch.hits.alloc(px * 32));
         CU(tr, PC_ERR_ALLOC, ch.emSamples.alloc(px * 16));
+        CU(tr, PC_ERR_ALLOC, ch.permOcc.alloc(px * 4));
+        CU(tr, PC_ERR_ALLOC, ch.permInd.alloc(px * 4));
         CU(tr, PC_ERR_ALLOC, ch.status.alloc(tr->statusStride * MAX_BOUNCES * 8));
         if (!ch.ctl.p) {
             CU(tr, PC_ERR_ALLOC, ch.ctl.alloc(sizeof(TraceCtl)));
@@ -389,6 +395,8 @@ int ensure_chains(pc_tracer *tr, int want) {
         ch.fb.hitFlags = (uint32_t *)ch.hitFlags.p;
         ch.fb.hits = (HitRec *)ch.hits.p;
         ch.fb.emissiveSamples = (float4 *)ch.emSamples.p;
+        ch.fb.permOcc = (uint32_t *)ch.permOcc.p;
+        ch.fb.permInd = (uint32_t *)ch.permInd.p;
         ch.fb.traceAcc = (float4 *)(c == 0 ? tr->traceAcc.p : ch.acc.p);
         DevBuf *zero[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status};
         for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
@@ -401,7 +409,7 @@ int ensure_chains(pc_tracer *tr, int want) {
 void release_chain_buffers(pc_tracer *tr) {
     for (int c = 0; c < MAX_CHAINS; c++) {
         Chain &ch = tr->chain[c];
-        DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.acc};
+        DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.acc, &ch.permOcc, &ch.permInd};
         for (DevBuf *b : all) b->release();
     }
     tr->nChains = 0;
@@ -558,6 +566,7 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_FIX_Q4: tr->optFixQ4 = value != 0; break;
         case PC_OPT_KERNEL_TIMERS: tr->optTimers = value != 0; break;
         case PC_OPT_FUSE_TRACE: tr->optFuse = value != 0; break;
+        case PC_OPT_SORT_RAYS: tr->optSort = value != 0; break;
         case PC_OPT_SAMPLE_CHAINS:
             if (value < 1 || value > MAX_CHAINS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample chains must be in [1, %d]", MAX_CHAINS);
             tr->optChains = value;
@@ -652,6 +661,12 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     s.texData = (const uint8_t *)tr->texData.p;
     s.numEmissives = (uint32_t)(v->emissives_bytes / 80);
     s.sceneDiffuseMat = v->scene_diffuse_mat_index;
+    {   // top-level root box -> 2 x 2 x 2 origin cells of the traversal-order sort key
+        const float *n0 = (const float *)v->bvh_nodes;  // {min.xyz, L}{max.xyz, R}
+        s.worldMin = make_float3(n0[0], n0[1], n0[2]);
+        auto cellScale = [](float lo, float hi) { return hi > lo ? 2.0f / (hi - lo) : 0.0f; };
+        s.worldCellScale = make_float3(cellScale(n0[0], n0[4]), cellScale(n0[1], n0[5]), cellScale(n0[2], n0[6]));
+    }
     tr->stackNeed = L.stack_need;
     tr->hasScene = true;
     tr->sceneEpoch++;
@@ -741,7 +756,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.chains = nc; key.fuse = tr->optFuse; key.sceneEpoch = tr->sceneEpoch; key.seedsPtr = tr->seedsDev.p;
+            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; key.sceneEpoch = tr->sceneEpoch; key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;
@@ -979,11 +994,11 @@ int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode, ui
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl, cnt, 12, cudaMemcpyHostToDevice, s));
     const int pg = tr->persistentGrid;
     if (mode == 0) {
-        if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0);
-        else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0);
+        if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0, nullptr);
+        else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0, nullptr);
     } else if (mode == 1) {
-        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0);
-        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0);
+        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0, nullptr);
+        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0, nullptr);
     } else if (mode == 2) {
         k_debug_packet<false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, n, 0);
     } else {

@@ -87,6 +87,7 @@ struct FrameBufs {
     HitRec *hits;
     float4 *emissiveSamples;
     float4 *traceAcc;
+    uint32_t *permOcc, *permInd;  // traversal order of rays[2] / of the next bounce's rays (PC_OPT_SORT_RAYS)
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
@@ -203,14 +204,16 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
 #if !PC_TRACE_REFILL
 // Fixed units: a warp pulls 32 consecutive rays and every lane walks its ray with traverse().
 template <bool ANY_HIT, bool COUNT, class Source, class Sink>
-__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink) {
+__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+                                            const uint32_t *perm = nullptr) {
     UnitClaim claim{0u};
     for (;;) {
         uint32_t size;
         const uint32_t unit = next_unit_adaptive(head, n, claim, size);
         if (unit >= n) break;
-        const uint32_t i = unit + lane_id();
-        if (lane_id() < size && i < n) {
+        const uint32_t j = unit + lane_id();
+        if (lane_id() < size && j < n) {
+            const uint32_t i = perm ? __ldcs(perm + j) : j;  // which ray a lane walks changes nothing: results go to slot i
             float3 o, d;
             float tmax;
             src.load(i, o, d, tmax);
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(D
 // rayIntersectionQuery over rays[a][0 .. numRays[a])
 template <bool REFERENCE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene sc, const Ray *rays, uint32_t *hitFlags, HitRec *hits,
-                                                     TraceCtl *ctl, int a, int queueSlot) {
+                                                     TraceCtl *ctl, int a, int queueSlot, const uint32_t *perm) {
     const uint32_t n = (uint32_t)ctl->numRays[a];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
     TravStats st{0, 0, 0};
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene
     if (!REFERENCE) {
         RaySource src{rays};
         HitSink<COUNT> sink{hitFlags, hits, 0u};
-        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
         missed = sink.missed;
     } else {
         for (;;) {
@@ -577,14 +580,14 @@ struct OcclusionSink {
 template <bool REFERENCE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
                                                          const float4 *emissiveSamples, float4 *acc, uint32_t *hitFlags,
-                                                         TraceCtl *ctl, int queueSlot) {
+                                                         TraceCtl *ctl, int queueSlot, const uint32_t *perm) {
     const uint32_t n = (uint32_t)ctl->numRays[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)n);
     TravStats st{0, 0, 0};
     OcclusionSink<COUNT> sink{rays, paths, emissiveSamples, acc, hitFlags, 0u};
     if (!REFERENCE) {
         RaySource src{rays};
-        trace_queue<true, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+        trace_queue<true, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
     } else {
         Trav dummy;
         for (;;) {
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
 // (pipeline.go:160-165 then :203-209).  Two queue heads: every warp drains the closest-hit queue first (the
 // longer walks), then the any-hit queue, whose cheap rays make the launch's tail.  Saves one launch tail per bounce.
 template <bool COUNT>
-__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot) {
+__global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot, int sorted) {
     const uint32_t nQ = (uint32_t)ctl->numRays[a], nO = (uint32_t)ctl->numRays[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)nQ);
@@ -628,8 +631,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
         uint32_t size;
         const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot], nQ + nO, claim, size);
         if (unit >= nQ) break;
-        const uint32_t i = unit + lane_id();
-        if (lane_id() < size && i < nQ) {
+        const uint32_t j = unit + lane_id();
+        if (lane_id() < size && j < nQ) {
+            const uint32_t i = sorted ? __ldcs(fb.permInd + j) : j;
             const Ray r = ld_ray(qrays + i);
             Hit best;
             const int hit = traverse<false, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
@@ -643,8 +647,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
         uint32_t size;
         const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot + 1], nO, claim, size);
         if (unit >= nO) break;
-        const uint32_t i = unit + lane_id();
-        if (lane_id() < size && i < nO) {
+        const uint32_t j = unit + lane_id();
+        if (lane_id() < size && j < nO) {
+            const uint32_t i = sorted ? __ldcs(fb.permOcc + j) : j;
             const Ray r = ld_ray(orays + i);
             Hit best;
             const int hit = traverse<true, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
@@ -749,6 +754,23 @@ constexpr int SHADE_TILE = SHADE_BLOCK * SHADE_RPT;
 constexpr int SHADE_GROUPS = SHADE_TILE / 32;
 static_assert(SHADE_GROUPS <= 32, "one warp scans the per-group counts");
 
+// Traversal-order key of an emitted ray (PC_OPT_SORT_RAYS): which octant of the scene it starts in, which octant it
+// points to, and its dominant axis.  k_shade writes the rays themselves in parent order (the order is part of the result:
+// it fixes every ray's random stream) and, next to them, a permutation of each tile's output range sorted by
+// this key; the traversal kernels pull their 32-ray units through it, so a warp walks rays that start close together and
+// point the same way.  Modelled on real bounce rays of config 2 (tools/simt_model.py): -19 % warp instructions for the
+// indirect rays, -25 % for the occlusion rays.
+constexpr int SORT_BINS = 256;
+__device__ __forceinline__ uint32_t sortKey(const DScene &sc, float ox, float oy, float oz, float dx, float dy, float dz) {
+    const uint32_t cx = (ox - sc.worldMin.x) * sc.worldCellScale.x >= 1.0f ? 1u : 0u;
+    const uint32_t cy = (oy - sc.worldMin.y) * sc.worldCellScale.y >= 1.0f ? 1u : 0u;
+    const uint32_t cz = (oz - sc.worldMin.z) * sc.worldCellScale.z >= 1.0f ? 1u : 0u;
+    const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    const uint32_t axis = ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u);
+    return ((cx | (cy << 1) | (cz << 2)) << 5) | (oct << 2) | axis;
+}
+
 struct ShadeShared {
     float occ[10][SHADE_TILE];   // origin.xyz, maxDist, dir.xyz, sample.xyz   (struct of arrays: conflict free)
     float ind[6][SHADE_TILE];    // origin.xyz, dir.xyz
@@ -758,6 +780,7 @@ struct ShadeShared {
     uint8_t flags[SHADE_TILE];    // bit 0 occlusion ray wanted, bit 1 indirect ray wanted
     uint32_t hist[SHADE_KEYS];    // per-key counts, then the keys' first positions in perm
     uint32_t groupOcc[SHADE_GROUPS], groupInd[SHADE_GROUPS];  // per 32-slot group: counts, then exclusive offsets
+    uint32_t binOcc[SORT_BINS], binInd[SORT_BINS];  // traversal-order sort of the emitted rays: per-key counts, then first positions
     uint32_t tile, occBase, indBase, nextChunk, activeChunks;
 };
 
@@ -768,14 +791,15 @@ struct ShadeShared {
 // / `/` in these very functions (Makefile: SHADE_FP).  The host side reaches it through these two functions.
 void shade_configure(const cudaDeviceProp &prop, int *blocksPerSM);
 void shade_launch(bool count, int grid, cudaStream_t s, const DScene &sc, const FrameBufs &fb, TraceCtl *ctl, const uint32_t *seeds,
-                  unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce, uint32_t minBouncesForRR, int a, int fixQ4);
+                  unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce, uint32_t minBouncesForRR, int a, int fixQ4,
+                  int sortRays);
 const char *shade_fp_mode();
 
 #ifdef PC_SHADE_TU
 template <bool COUNT>
 __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
                                                       unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce,
-                                                      uint32_t minBouncesForRR, int a, int fixQ4) {
+                                                      uint32_t minBouncesForRR, int a, int fixQ4, int sortRays) {
     extern __shared__ __align__(16) unsigned char shade_smem[];
     ShadeShared &sh = *reinterpret_cast<ShadeShared *>(shade_smem);
     const unsigned FULL = 0xFFFFFFFFu;
@@ -802,6 +826,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         __syncthreads();  // the previous tile's shared state is no longer in use
         if (tid == 0) { sh.tile = atomicAdd(&ctl->ticket[bounce], 1u); sh.nextChunk = 0u; }
         if (tid < SHADE_KEYS) sh.hist[tid] = 0u;
+        if (sortRays) { sh.binOcc[tid] = 0; sh.binInd[tid] = 0; }  // SORT_BINS == SHADE_BLOCK
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= nTiles) break;
@@ -907,6 +932,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         // ---- 4. stable compaction in original order (replaces pt_integrator.cl:162,176,188-197): warp w owns the
         //         32-slot groups w, w + SHADE_WARPS, ...
         unsigned occMask[SHADE_RPT], indMask[SHADE_RPT];
+        uint32_t sortOcc[SHADE_RPT], sortInd[SHADE_RPT];  // key | rank inside the key's bin << 8
 #pragma unroll
         for (int r = 0; r < SHADE_RPT; r++) {
             if ((uint32_t)r >= rpt) break;
@@ -915,8 +941,35 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             occMask[r] = __ballot_sync(FULL, (f & 1u) != 0u);
             indMask[r] = __ballot_sync(FULL, (f & 2u) != 0u);
             if (lane == 0) { sh.groupOcc[g] = (uint32_t)__popc(occMask[r]); sh.groupInd[g] = (uint32_t)__popc(indMask[r]); }
+            sortOcc[r] = 0u; sortInd[r] = 0u;
+            if (sortRays) {  // key, and the arrival rank inside the key's bin
+                const uint32_t slot = g * 32u + lane;
+                if (f & 1u) {
+                    const uint32_t k = sortKey(sc, sh.occ[0][slot], sh.occ[1][slot], sh.occ[2][slot], sh.occ[4][slot], sh.occ[5][slot], sh.occ[6][slot]);
+                    sortOcc[r] = k | (atomicAdd(&sh.binOcc[k], 1u) << 8);
+                }
+                if (f & 2u) {
+                    const uint32_t k = sortKey(sc, sh.ind[0][slot], sh.ind[1][slot], sh.ind[2][slot], sh.ind[3][slot], sh.ind[4][slot], sh.ind[5][slot]);
+                    sortInd[r] = k | (atomicAdd(&sh.binInd[k], 1u) << 8);
+                }
+            }
         }
         __syncthreads();
+        if (sortRays && (warp == 1 || warp == 2)) {  // exclusive scans of the two 256-entry bin tables, 8 entries per lane
+            uint32_t *bins = warp == 1 ? sh.binOcc : sh.binInd;
+            uint32_t v[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { v[k] = bins[lane * 8 + k]; sum += v[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += o;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { bins[lane * 8 + k] = run; run += v[k]; }
+        }
         if (warp == 0) {
             const uint32_t groups = rpt * SHADE_WARPS;
             const uint32_t o = lane < groups ? sh.groupOcc[lane] : 0u, q = lane < groups ? sh.groupInd[lane] : 0u;
@@ -953,11 +1006,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 __stcs(fb.emissiveSamples + k, make_float4(sh.occ[7][slot], sh.occ[8][slot], sh.occ[9][slot], 0.0f));
                 st_ray(fb.rays[2] + k, make_float4(sh.occ[0][slot], sh.occ[1][slot], sh.occ[2][slot], sh.occ[3][slot]),
                        make_float4(sh.occ[4][slot], sh.occ[5][slot], sh.occ[6][slot], pif));
+                if (sortRays) fb.permOcc[sh.occBase + sh.binOcc[sortOcc[r] & 0xFFu] + (sortOcc[r] >> 8)] = k;
             }
             if (indMask[r] & (1u << lane)) {  // :207-210
                 const uint32_t k = sh.indBase + sh.groupInd[g] + (uint32_t)__popc(indMask[r] & ltMask);
                 st_ray(fb.rays[1 - a] + k, make_float4(sh.ind[0][slot], sh.ind[1][slot], sh.ind[2][slot], FLT_MAX),
                        make_float4(sh.ind[3][slot], sh.ind[4][slot], sh.ind[5][slot], pif));
+                if (sortRays) fb.permInd[sh.indBase + sh.binInd[sortInd[r] & 0xFFu] + (sortInd[r] >> 8)] = k;
             }
         }
     }

@@ -12,6 +12,8 @@
 
 namespace pc {
 
+static_assert(SORT_BINS == SHADE_BLOCK, "k_shade clears one bin per thread");
+
 const char *shade_fp_mode() { return PC_SHADE_FP_MODE; }
 
 void shade_configure(const cudaDeviceProp &prop, int *blocksPerSM) {
@@ -32,11 +34,12 @@ void shade_configure(const cudaDeviceProp &prop, int *blocksPerSM) {
 }
 
 void shade_launch(bool count, int grid, cudaStream_t s, const DScene &sc, const FrameBufs &fb, TraceCtl *ctl, const uint32_t *seeds,
-                  unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce, uint32_t minBouncesForRR, int a, int fixQ4) {
+                  unsigned long long *status, uint32_t seedsPerSample, uint32_t bounce, uint32_t minBouncesForRR, int a, int fixQ4,
+                  int sortRays) {
     if (count)
-        k_shade<true><<<grid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(sc, fb, ctl, seeds, status, seedsPerSample, bounce, minBouncesForRR, a, fixQ4);
+        k_shade<true><<<grid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(sc, fb, ctl, seeds, status, seedsPerSample, bounce, minBouncesForRR, a, fixQ4, sortRays);
     else
-        k_shade<false><<<grid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(sc, fb, ctl, seeds, status, seedsPerSample, bounce, minBouncesForRR, a, fixQ4);
+        k_shade<false><<<grid, SHADE_BLOCK, sizeof(ShadeShared), s>>>(sc, fb, ctl, seeds, status, seedsPerSample, bounce, minBouncesForRR, a, fixQ4, sortRays);
 }
 
 }  // namespace pc

@@ -153,13 +153,14 @@ def test_full_depth_single_sample(key, w, h):
 
 def test_variants_bit_identical():
     """packet vs per-ray primary traversal, graph replay vs direct launches, counters on/off, the fused
-    occlusion + query launch and the reference-order traversal all produce the same accumulator bits (GPU vs GPU)."""
+    occlusion + query launch, the sorted traversal order and the reference-order traversal all produce the same accumulator bits (GPU vs GPU)."""
     w = h = 160
     sc = C.small_scene("c2", w, h)
     seeds = T.splitmix_seeds(5, 2 * 6)
     ref = None
     for opts in ({}, {"primary_packets": 0}, {"use_graph": 0}, {"counters": 1}, {"reference_order": 1}, {"fuse_trace": 0},
-                 {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}):
+                 {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}, {"sort_rays": 1},
+                 {"sort_rays": 0}, {"sort_rays": 1, "fuse_trace": 0}, {"sort_rays": 1, "counters": 1, "use_graph": 0}):
         cu = C.cuda_for(sc, w, h, **opts)
         cu.trace(T.make_block_request(w, h, spp=2), seeds)
         acc = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
