@@ -749,6 +749,10 @@ PC_HD void travInit(Trav &t, const DScene &sc, float3 o0, float3 d0, float tmaxR
     t.sp = 0;
 }
 
+// Reference classes: inner node (bit 31 clear), triangle leaf (bits 31:30 == 10), and the "other"
+// leaf-type references with bits 31:30 == 11 (instance entry, the exit marker, REF_DONE).
+PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
+
 // One inner-node step: slab-test both children (one aligned 64 B record), descend into the nearer
 // accepted child, push the other.  Requires !(t.cur & REF_LEAF).
 template <bool ANY_HIT, bool COUNT>
@@ -767,8 +771,14 @@ PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) 
     uint32_t lref = f2u(q0.w), rref = f2u(q1.w);
     if (wl && wr) {
         bool leftFirst = tl <= tr;
-        stack[t.sp++] = leftFirst ? rref : lref;
+        const uint32_t farRef = leftFirst ? rref : lref;
+        stack[t.sp++] = farRef;
         t.cur = leftFirst ? lref : rref;
+#if defined(__CUDA_ARCH__) && defined(PC_PREFETCH_FAR)
+        // the far child is fetched when it is popped, many steps later: ask for its record now (experiment)
+        if (!(farRef & REF_LEAF)) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.node64 + 4 * (size_t)farRef));
+        else if (refIsTriLeaf(farRef)) asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.tri48 + 3 * (size_t)(farRef & 0x3FFFFFFFu)));
+#endif
     } else if (wl || wr) {
         t.cur = wl ? lref : rref;
     } else {
@@ -776,9 +786,6 @@ PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) 
     }
 }
 
-// Reference classes: inner node (bit 31 clear), triangle leaf (bits 31:30 == 10), and the "other"
-// leaf-type references with bits 31:30 == 11 (instance entry, the exit marker, REF_DONE).
-PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
 
 // Instance entry (:237-249) or the exit marker that restores the world-space ray (:330-335).
 // Returns 0 to continue, 1 when the walk is over.  Requires bits 31:30 == 11 and cur != REF_DONE.
