@@ -268,6 +268,57 @@ def workload_config(n, w, h, spp, config="c2", sc=None):
             "l2": "per-step ray/path state (220 B/px x frame, re-written every bounce) exceeds the 126 MB L2; scene data is L2 resident by design"}
 
 
+def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, use_traffic):
+    """A second pass of the same workload in PC_OPT_KERNEL_TIMERS mode (CUDA events around every launch on the tracer's
+    stream, one sample chain) with device counters on: algorithmic bytes of the dominant kernel class / its measured time."""
+    from polaris_b200 import _lib
+    from polaris_b200 import tracer as T
+
+    tr.set_option(_lib.OPT_KERNEL_TIMERS, 1)
+    tr.set_option(_lib.OPT_COUNTERS, 1)
+    req = T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=prof_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR,
+                               exposure=EXPOSURE)
+    tr.trace(req, seeds[: prof_spp * (1 + NUM_BOUNCES)])
+    tr.set_option(_lib.OPT_KERNEL_TIMERS, 0)
+    tr.set_option(_lib.OPT_COUNTERS, 0)
+    st = tr.stats().device
+    st["_spp"], st["_background"] = prof_spp, sc.scene_diffuse_mat_index != -1
+    by = algorithmic_bytes(st, w * block_h, NUM_BOUNCES)
+    times = {n: st["kernel_time_ns"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
+    counts = {n: st["kernel_count"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
+    total_ns = sum(times.values())
+    if counts.get("k_trace"):
+        # PC_OPT_FUSE_TRACE: the occlusion test and the next bounce's query share a launch, and the device
+        # counters are per trace call, not per launch: report the two traversal classes as one ("k_trace" =
+        # the fused launches + the last bounce's stand-alone k_occlusion)
+        by["k_trace"] = by.pop("k_query") + by.pop("k_occlusion")
+        times["k_trace"] += times.pop("k_query") + times.pop("k_occlusion")
+        counts["k_trace"] += counts.pop("k_query") + counts.pop("k_occlusion")
+    classes = [k for k in ("k_primary", "k_shade", "k_occlusion", "k_query", "k_trace") if counts.get(k)]
+    dom = max(classes, key=lambda k: times[k])
+    peak, peak_src = measured_hbm_peak()
+    kern = {}
+    for k in classes:
+        if counts[k]:
+            kern[k] = {"launches": counts[k], "avg_us": times[k] / counts[k] / 1e3, "share": times[k] / max(1, total_ns),
+                       "alg_GBps": by[k] / max(1, times[k])}
+    log("[bench] kernel classes: " + json.dumps(kern))
+    achieved = by[dom] / max(1, times[dom])  # bytes per ns == GB/s
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and use_traffic:  # the ncu capture was taken on config 2
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    rays = st["query_rays"] + st["occlusion_rays"]
+    return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / max(1, counts[dom]),
+            "avg_launch_us": times[dom] / max(1, counts[dom]) / 1e3, "kernels": kern,
+            "rays_per_path": rays / (w * block_h * prof_spp), "nodes_per_ray": st["nodes_tested"] / max(1, rays),
+            "tris_per_ray": st["tris_tested"] / max(1, rays)}
+
+
 # ------------------------------------------------------------------------------------------------
 def run_cuda_single(args):
     import torch  # device plumbing only (event/synchronize helpers are not needed; kept for parity with N>1)
@@ -341,47 +392,7 @@ def run_cuda_single(args):
     d2h = w * h * 4
 
     # ---- roofline pass: same workload, per-kernel CUDA events + device counters
-    tr.set_option(_lib.OPT_KERNEL_TIMERS, 1)
-    tr.set_option(_lib.OPT_COUNTERS, 1)
-    prof_spp = min(spp, 32)
-    req = T.make_block_request(w, h, spp=prof_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
-    tr.trace(req, seeds[: prof_spp * (1 + NUM_BOUNCES)])
-    st = tr.stats().device
-    st["_spp"], st["_background"] = prof_spp, sc.scene_diffuse_mat_index != -1
-    by = algorithmic_bytes(st, w * h, NUM_BOUNCES)
-    times = {n: st["kernel_time_ns"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
-    counts = {n: st["kernel_count"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
-    total_ns = sum(times.values())
-    if counts.get("k_trace"):
-        # PC_OPT_FUSE_TRACE: the occlusion test and the next bounce's query share a launch, and the device
-        # counters are per trace call, not per launch: report the two traversal classes as one ("k_trace" =
-        # the fused launches + the last bounce's stand-alone k_occlusion)
-        by["k_trace"] = by.pop("k_query") + by.pop("k_occlusion")
-        times["k_trace"] += times.pop("k_query") + times.pop("k_occlusion")
-        counts["k_trace"] += counts.pop("k_query") + counts.pop("k_occlusion")
-    classes = [k for k in ("k_primary", "k_shade", "k_occlusion", "k_query", "k_trace") if counts.get(k)]
-    dom = max(classes, key=lambda k: times[k])
-    peak, peak_src = measured_hbm_peak()
-    kern = {}
-    for k in classes:
-        if counts[k]:
-            kern[k] = {"launches": counts[k], "avg_us": times[k] / counts[k] / 1e3, "share": times[k] / max(1, total_ns),
-                       "alg_GBps": by[k] / max(1, times[k])}
-    log("[bench] kernel classes: " + json.dumps(kern))
-    achieved = by[dom] / max(1, times[dom])  # bytes per ns == GB/s
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and args.config == "c2":  # the ncu capture was taken on config 2
-        try:
-            traffic = json.load(open(tp)).get(dom)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / max(1, counts[dom]),
-                "avg_launch_us": times[dom] / max(1, counts[dom]) / 1e3, "kernels": kern,
-                "rays_per_path": (st["query_rays"] + st["occlusion_rays"]) / (w * h * prof_spp),
-                "nodes_per_ray": st["nodes_tested"] / max(1, st["query_rays"] + st["occlusion_rays"]),
-                "tris_per_ray": st["tris_tested"] / max(1, st["query_rays"] + st["occlusion_rays"])}
+    roofline = roofline_pass(tr, sc, w, h, 0, h, min(spp, 32), seeds, use_traffic=args.config == "c2")
     tr.close()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
@@ -565,6 +576,11 @@ def run_cuda_multi(args):
     e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e_dt, op=dist.ReduceOp.MAX)
     e_dt = float(e_dt.item())
+    roofline = None
+    if rank == 0:  # rank 0's own row block of the last assignment, per-kernel CUDA events (the other ranks are done)
+        rows_last = [int(sp.block_h) for sp in speeds]
+        roofline = roofline_pass(tr, sc, w, h, 0, max(1, rows_last[0]), min(pass_spp, 16), seeds, use_traffic=False)
+        roofline["note"] = f"rank 0's block ({rows_last[0]} rows of {h}) of the last row assignment"
     if rank == 0:
         line = {
             "metric": "Mrays/s (all bounces)", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -574,7 +590,7 @@ def run_cuda_multi(args):
             "clocks": clk, "rows_last_step": [int(s.block_h) for s in speeds],
             "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s",
                     "h2d_bytes_per_step": int((sc.nbytes() + seeds.nbytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
-            "roofline": None, "cpu_baseline": None, "one_gpu_same_workload": one_gpu,
+            "roofline": roofline, "cpu_baseline": None, "one_gpu_same_workload": one_gpu,
         }
         emit(line)
     tr.close()
