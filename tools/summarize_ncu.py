@@ -51,8 +51,15 @@ for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
     try:
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
         tb = [float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1) for r in rows[:2]]
         traffic[k] = sum(tb) / len(tb)
+        # derived: achieved HBM and L2 GB/s under the profiler (cold caches, serialised launches)
+        it, il = hdr.index("gpu__time_duration.sum"), hdr.index("lts__t_sectors.sum")
+        secs = [float(r[it]) * tscale.get(units[it], 1e-9) for r in rows[:2]]
+        l2 = [float(r[il]) * 32.0 for r in rows[:2]]  # 32-byte sectors
+        md.append("derived: HBM " + " / ".join(f"{b / t / 1e9:.0f}" for b, t in zip(tb, secs)) + " GB/s, L2 "
+                  + " / ".join(f"{b / t / 1e9:.0f}" for b, t in zip(l2, secs)) + " GB/s (launch 1 / launch 2)\n")
     except Exception:
         pass
 os.makedirs(P, exist_ok=True)
