@@ -84,3 +84,23 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in text.replace("the CPU oracle", "").replace("oracle's", "").replace("with the oracle", "")\
                     .replace("CPU oracle", "").replace("and the oracle", "").replace("oracle comparison", "").replace("the oracle", ""), \
                     f"{f} mentions the oracle package"
+
+
+def _build_c_client(tmp_path):
+    """gcc -std=c99 against include/polaris_cuda.h + libpolaris_cuda.so: what a cgo binding compiles and links against."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "render_frame")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "cabi", "render_frame.c"), "-L", os.path.join(root, "polaris_b200"), "-lpolaris_cuda",
+                    "-Wl,-rpath," + os.path.join(root, "polaris_b200")], check=True)
+    return exe
+
+
+def test_c99_client_compiles_and_links(tmp_path):
+    import subprocess
+
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage" in r.stderr  # no GPU work without arguments

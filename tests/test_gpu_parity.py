@@ -514,3 +514,33 @@ def test_debug_stages_golden(key):
     want = [(int(f), int(b), fr) for f, b, fr in zip(g["flags"], g["bounces"], g["frames"])]
     _assert_frames_close(got, want, f"golden {key}")
     cu.close()
+
+
+def test_c99_client_renders_the_same_frame(tmp_path):
+    """tests/cabi/render_frame.c (plain C over the C ABI, scene from a PLRSCN2 dump) == the Python binding, byte for byte."""
+    import subprocess
+
+    from .test_cpu_abi import _build_c_client
+
+    w = h = 128
+    spp = 4
+    sc = C.small_scene("c2", w, h)
+    dump = str(tmp_path / "c2.plrscn")
+    sc.save(dump)
+    exe, out = _build_c_client(tmp_path), str(tmp_path / "frame.ppm")
+    cam = [repr(float(x)) for x in np.asarray(sc.camera.frustrum, np.float32).reshape(16)] + [repr(float(x)) for x in np.asarray(sc.camera.position, np.float32)]
+    r = subprocess.run([exe, dump, str(w), str(h), str(spp), out] + cam, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    print("C client:", r.stdout.strip())
+    raw = open(out, "rb").read()
+    hdr = f"P6\n{w} {h}\n255\n".encode()
+    assert raw.startswith(hdr)
+    got = np.frombuffer(raw[len(hdr):], np.uint8).reshape(h, w, 3)
+    cu = C.cuda_for(sc, w, h)
+    req = T.make_block_request(w, h, spp=spp)
+    cu.trace(req, T.splitmix_seeds(2, spp * 6))
+    cu.merge_output(cu, req)
+    cu.sync_framebuffer(T.make_block_request(w, h, spp=spp))
+    assert np.array_equal(cu.frame_buffer[..., :3], got)
+    assert got.any()
+    cu.close()
