@@ -544,3 +544,93 @@ def test_c99_client_renders_the_same_frame(tmp_path):
     assert np.array_equal(cu.frame_buffer[..., :3], got)
     assert got.any()
     cu.close()
+
+
+# --------------------------------------------------------------------------------------------
+# edge cases: ragged frames, one-row blocks, empty work, all-miss frames, bounce-count extremes
+# --------------------------------------------------------------------------------------------
+def _compare_traces(sc, w, h, req_kwargs, seeds, what, tol=1e-3, cam=None, **opts):
+    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h, counters=1, **opts)
+    if cam is not None:
+        for tr in (orc, cu):
+            tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, cam)
+    ro, rg = T.make_block_request(w, h, **req_kwargs), T.make_block_request(w, h, **req_kwargs)
+    orc.trace(ro, seeds)
+    cu.trace(rg, seeds)
+    assert (rg.seed, rg.accumulated_samples) == (ro.seed, ro.accumulated_samples)
+    a, b = C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h), C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h)
+    _assert_close_pixels(a, b, tol, what)
+    so, sg = orc.stats().device, cu.stats().device
+    for k in ("query_rays", "occlusion_rays"):
+        assert abs(so[k] - sg[k]) <= max(4, int(2e-3 * so[k])), (what, k, so[k], sg[k])
+    cnt = (cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32), orc.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32))
+    orc.close()
+    cu.close()
+    return a, b, sg, cnt
+
+
+def test_ragged_frames_and_blocks():
+    """Frame sizes that are no multiple of a warp, a packet tile (8x4), a shade tile (1024) or a traversal unit, one-row
+    blocks, a sample count below the number of sample chains: every partially filled unit / tile path."""
+    for (w, h), kw, opts in (((97, 61), dict(spp=3), {}), ((97, 61), dict(spp=3), {"primary_packets": 1}), ((33, 7), dict(spp=5, num_bounces=2), {}),
+                             ((64, 64), dict(block_y=63, block_h=1, spp=2), {"fix_q4": 1}), ((130, 9), dict(block_y=3, block_h=5, spp=1), {"sample_chains": 8}),
+                             ((1, 1), dict(spp=4), {})):
+        sc = C.small_scene("c2", w, h)
+        seeds = T.splitmix_seeds(3, kw["spp"] * (1 + kw.get("num_bounces", 5)))
+        a, b, st, _ = _compare_traces(sc, w, h, kw, seeds, f"{w}x{h} {kw} {opts}", **opts)
+        by, bh = kw.get("block_y", 0), kw.get("block_h", h)
+        outside = np.ones(h, bool)
+        outside[by:by + bh] = False
+        assert a.reshape(h, w, 3)[outside].sum() == 0  # nothing leaks out of the block's rows
+        assert st["query_rays"] >= w * bh * kw["spp"]
+
+
+def test_no_work_and_all_miss():
+    w = h = 64
+    sc = C.small_scene("c2", w, h)
+    cu = C.cuda_for(sc, w, h, counters=1)
+    # zero samples: nothing traced, the request is unchanged, the accumulator is cleared
+    req = T.make_block_request(w, h, spp=0, accumulated_samples=7)
+    cu.trace(req, np.zeros(0, np.uint32))
+    assert req.accumulated_samples == 7 and cu.stats().device["query_rays"] == 0
+    assert not C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h).any()
+    cu.close()
+    # a camera that looks away from everything: every primary ray misses, the later stages see empty queues
+    import copy
+    for key in ("c2", "c4"):  # without / with a background (scene diffuse) material
+        sc = C.small_scene(key, w, h)
+        cam = copy.deepcopy(sc.camera)
+        cam.position = np.array([0.0, 1000.0, 0.0], np.float32)
+        cam.look_at = np.array([0.0, 2000.0, 1.0], np.float32)
+        cam.update()
+        a, b, st, cnt = _compare_traces(sc, w, h, dict(spp=2), T.splitmix_seeds(4, 12), f"{key} all primary rays miss", tol=1e-4, cam=cam)
+        assert st["query_rays"] == w * h * 2 and st["occlusion_rays"] == 0 and st["missed_query_rays"] == w * h * 2
+        assert cnt[0].tolist() == cnt[1].tolist() and cnt[0][1] == 0 and cnt[0][2] == 0
+        assert a.any() == (sc.scene_diffuse_mat_index != -1)
+
+
+@pytest.mark.parametrize("nb,rr", [(1, 0), (2, 0), (8, 1), (12, 3)])
+def test_bounce_count_and_roulette_extremes(nb, rr):
+    w = h = 96
+    sc = C.small_scene("c2", w, h)
+    seeds = T.splitmix_seeds(6, 2 * (1 + nb))
+    allowed_scale = 1 + nb // 4  # pixels that took another branch stay different for the rest of the path
+    orc, cu = C.oracle_for(sc, w, h), C.cuda_for(sc, w, h)
+    ro = T.make_block_request(w, h, spp=2, num_bounces=nb, min_bounces_for_rr=rr)
+    rg = T.make_block_request(w, h, spp=2, num_bounces=nb, min_bounces_for_rr=rr)
+    orc.trace(ro, seeds)
+    cu.trace(rg, seeds)
+    a, b = C.acc_of(cu, _lib.BUF_TRACE_ACCUMULATOR, w, h), C.acc_of(orc, _lib.BUF_TRACE_ACCUMULATOR, w, h)
+    err = C.rel_err(a, b)
+    bad = int((err > 1e-3).sum())
+    print(f"{nb} bounces, roulette from {rr}: {bad} / {len(err)} pixels beyond 1e-3")
+    assert bad <= max(2, int(OUTLIER_FRACTION * len(err))) * allowed_scale
+    so, sg = orc.stats().device, cu.stats().device
+    assert abs(so["query_rays"] - sg["query_rays"]) <= max(4, int(2e-3 * so["query_rays"]))
+    assert sg["kernel_launches"] == 2 + 2 * (2 + 2 * nb) + (1 if 2 > 1 else 0)  # 2 samples on 2 chains: begin, primary, nb shade, nb-1 fused, 1 occlusion; + the chain merge
+    with pytest.raises(T.TracerError):
+        cu.trace(T.make_block_request(w, h, num_bounces=33), None)  # MAX_BOUNCES = 32
+    with pytest.raises(T.TracerError):
+        cu.trace(T.make_block_request(w, h, num_bounces=0), None)
+    orc.close()
+    cu.close()
