@@ -37,17 +37,23 @@ thread_local std::string g_create_error;
 
 struct DevBuf {
     void *p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0;  // logical size (what pc_read_buffer may return)
+    size_t cap = 0;    // allocated size
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
         bytes = 0;
+        cap = 0;
     }
     cudaError_t alloc(size_t n) {
-        release();
         if (n == 0) n = 16;  // keep pointers non-null for empty tables
+        if (p && n <= cap && n * 2 >= cap) {  // re-uploading a scene of the same size: no cudaFree / cudaMalloc round trip
+            bytes = n;
+            return cudaSuccess;
+        }
+        release();
         cudaError_t e = cudaMalloc(&p, n);
-        if (e == cudaSuccess) bytes = n;
+        if (e == cudaSuccess) bytes = cap = n;
         return e;
     }
 };
@@ -618,7 +624,7 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     if (v->scene_diffuse_mat_index >= (int64_t)nMat) return fail(tr, PC_ERR_BAD_SCENE, "scene diffuse material index out of range");
     pc_layout::Builder lb((const pc_layout::RefNode *)v->bvh_nodes, v->bvh_nodes_bytes / 32,
                           (const pc_layout::RefInstance *)v->mesh_instances, v->mesh_instances_bytes / 80,
-                          (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16);
+                          (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16, /*derive_tris=*/false);
     pc_layout::Layout L = lb.build();
     if (!L.error.empty()) return fail(tr, PC_ERR_BAD_SCENE, "%s", L.error.c_str());
     if (L.stack_need > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
@@ -641,7 +647,16 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     if ((rc = upload(tr, tr->matIdx, v->material_indices, v->material_indices_bytes))) return rc;
     if ((rc = upload(tr, tr->emissives, v->emissives, v->emissives_bytes))) return rc;
     if ((rc = upload(tr, tr->node64, L.node64.data(), L.node64.size() * 16))) return rc;
-    if ((rc = upload(tr, tr->tri48, L.tri48.data(), L.tri48.size() * 16))) return rc;
+    {   // tri48 is derived on the device from the vertices and BVH nodes uploaded above
+        const size_t nTris = v->vertices_bytes / 48, nNodes = v->bvh_nodes_bytes / 32;
+        CU(tr, PC_ERR_ALLOC, tr->tri48.alloc(nTris * 48));
+        if (nTris) {
+            const int blocks = tr->prop.multiProcessorCount * 8;
+            k_derive_tri48<<<blocks, 256, 0, tr->stream>>>((const float4 *)tr->verts.p, (float4 *)tr->tri48.p, nTris);
+            k_leaf_counts<<<blocks, 256, 0, tr->stream>>>((const float4 *)tr->bvh.p, nNodes, (float4 *)tr->tri48.p, nTris);
+            CU(tr, PC_ERR_KERNEL, cudaGetLastError());
+        }
+    }
     if ((rc = upload(tr, tr->inst80, L.inst80.data(), L.inst80.size() * 16))) return rc;
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaStreamSynchronize(tr->stream));  // host vectors die with this scope
     DScene &s = tr->sc;

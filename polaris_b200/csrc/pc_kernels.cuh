@@ -1023,6 +1023,34 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
 
 #ifndef PC_SHADE_TU
 // ------------------------------------------------------------------------------------------------
+// tri48 on the device (pc_layout.hpp describes the record): the same float32 subtractions intersect.cl:255-256 does per
+// test, from the vertices that were uploaded anyway, and the "triangles left in this leaf" lane from the BVH's mesh leaves
+// ({min, -firstTriangle}{max, count}, optimized_scene.go:46-64).  Replaces a 48 B/triangle host pass + upload (0.5 GB for the
+// 10 M-triangle terrain) when a scene is (re)uploaded.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_derive_tri48(const float4 *__restrict__ vertices, float4 *__restrict__ tri48, size_t nTris) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < nTris; t += stride) {
+        const float4 v0 = vertices[3 * t], v1 = vertices[3 * t + 1], v2 = vertices[3 * t + 2];
+        tri48[3 * t] = make_float4(v0.x, v0.y, v0.z, 0.0f);
+        tri48[3 * t + 1] = make_float4(v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, 0.0f);
+        tri48[3 * t + 2] = make_float4(v2.x - v0.x, v2.y - v0.y, v2.z - v0.z, 0.0f);
+    }
+}
+__global__ void k_leaf_counts(const float4 *__restrict__ bvhNodes, size_t nNodes, float4 *__restrict__ tri48, size_t nTris) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nNodes; i += stride) {
+        const int l = __float_as_int(bvhNodes[2 * i].w), r = __float_as_int(bvhNodes[2 * i + 1].w);
+        if (l <= 0 && r > 0) {  // mesh leaf: triangles [-l, -l + r); reachable leaves were validated on the host, unreachable
+                                // nodes (meshes nobody instances) are only guarded
+            const size_t first = (size_t)(-(long long)l);
+            if (first + (size_t)r > nTris) continue;
+            for (int j = 0; j < r; j++) tri48[3 * (first + j)].w = __uint_as_float((uint32_t)(r - j));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // accumulator.cl:5-19, hdr.cl:5-28
 // ------------------------------------------------------------------------------------------------
 __global__ void k_clear(float4 *acc, size_t n) {

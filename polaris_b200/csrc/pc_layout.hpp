@@ -68,9 +68,13 @@ struct Layout {
 
 class Builder {
   public:
+    // derive_tris = false: the caller builds tri48 itself (the CUDA library does it on the device from the uploaded
+    // vertices and BVH nodes, saving a 48 B/triangle host pass and upload); everything else, including the validation of
+    // every leaf's triangle range, still happens here.
     Builder(const RefNode *nodes, size_t n_nodes, const RefInstance *inst, size_t n_inst, const Q *vertices,
-            size_t n_vertices)
-        : nodes_(nodes), n_nodes_(n_nodes), inst_(inst), n_inst_(n_inst), verts_(vertices), n_tris_(n_vertices / 3) {}
+            size_t n_vertices, bool derive_tris = true)
+        : nodes_(nodes), n_nodes_(n_nodes), inst_(inst), n_inst_(n_inst), verts_(vertices), n_tris_(n_vertices / 3),
+          derive_tris_(derive_tris) {}
 
     Layout build() {
         Layout L;
@@ -79,8 +83,9 @@ class Builder {
             L.error = "scene has no BVH nodes";
             return L;
         }
-        L.tri48.assign(3 * n_tris_, Q{0, 0, 0, 0});
-        for (size_t t = 0; t < n_tris_; t++) {
+        if (derive_tris_) L.tri48.assign(3 * n_tris_, Q{0, 0, 0, 0});
+        L.node64.reserve(2 * n_nodes_ + 4);  // at most (n_nodes - 1) / 2 inner nodes, 4 records each
+        for (size_t t = 0; derive_tris_ && t < n_tris_; t++) {
             const Q &v0 = verts_[3 * t], &v1 = verts_[3 * t + 1], &v2 = verts_[3 * t + 2];
             L.tri48[3 * t] = Q{v0.x, v0.y, v0.z, u2f(0)};
             L.tri48[3 * t + 1] = Q{v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, 0.f};  // edge01 (intersect.cl:255)
@@ -135,6 +140,7 @@ class Builder {
     size_t n_inst_;
     const Q *verts_;
     size_t n_tris_;
+    bool derive_tris_ = true;
     Layout *out_ = nullptr;
     uint32_t rank_ = 0;
     std::vector<uint8_t> inst_seen_;
@@ -182,7 +188,7 @@ class Builder {
                 L.error = "leaf triangle range out of bounds";
                 return 0;
             }
-            for (uint32_t j = 0; j < count; j++) L.tri48[3 * (size_t)(first + j)].w = u2f(count - j);
+            for (uint32_t j = 0; derive_tris_ && j < count; j++) L.tri48[3 * (size_t)(first + j)].w = u2f(count - j);
             return REF_LEAF | first;
         }
         if (n.r <= 0) {
