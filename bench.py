@@ -412,6 +412,7 @@ def run_cuda_single(args):
     line = {
         "metric": "Mrays/s (all bounces)", "value": value, "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "device_ms_per_step": tot_dev_ns / args.steps / 1e6,  # CUDA events around pc_trace on the tracer's stream (the rest of a step is merge + tonemap)
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp, args.config, sc),
         "spp_mpix_per_s": w * h * spp * args.steps / dt / 1e6, "gpu_launches": int(tot_launch), "clocks": clk,
         "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -474,6 +475,7 @@ def run_cuda_multi(args):
                 speeds[r].set_stats(int(res[r][0]), float(res[r][1]))
             totals["rays"] += sum(x[2] for x in res)
             totals["launches"] += sum(x[3] for x in res)
+            totals["device_ns"] = totals.get("device_ns", 0.0) + max(x[4] for x in res)  # CUDA-event time of pc_trace, max over ranks
             if rank == 0 and args.verbose:
                 log(f"[bench] pass: rows {[int(x[0]) for x in res]} trace ms {[round(x[1] * 1e3, 1) for x in res]}")
 
@@ -516,7 +518,7 @@ def run_cuda_multi(args):
         if rank == 0:
             tr.merge_output(tr, req)
         pending_gather.append((RowGather(rows, w, rank, world).start(mine, recv_bufs[(acc_samples // pass_spp) % 2]), rows, acc_samples, e2e))
-        pending_stats.append(StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"]], world, "cuda"))
+        pending_stats.append(StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"], d["device_time_ns"]], world, "cuda"))
         acc_samples += pass_spp
 
     # the SAME workload on ONE of these GPUs (rank 0 traces the whole frame, the others wait): the N = 1 default of this
@@ -548,14 +550,14 @@ def run_cuda_multi(args):
         clocks.start()
     dist.barrier()
     torch.cuda.synchronize()
-    totals["rays"] = totals["launches"] = 0.0
+    totals["rays"] = totals["launches"] = totals["device_ns"] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     drain()  # the last pass's rows are gathered, added and tonemapped inside the timed region
     dist.barrier()
     torch.cuda.synchronize()
-    rays, launches = totals["rays"], totals["launches"]
+    rays, launches, device_ns = totals["rays"], totals["launches"], totals["device_ns"]
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
@@ -585,6 +587,7 @@ def run_cuda_multi(args):
         line = {
             "metric": "Mrays/s (all bounces)", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "device_ms_per_step": device_ns / args.steps / 1e6,  # CUDA-event time of pc_trace, max over ranks, per pass
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, w, h, 1024),
             "spp_mpix_per_s": w * h * pass_spp * args.steps / dt / 1e6, "gpu_launches": int(launches) + 2 * args.steps * world,
             "clocks": clk, "rows_last_step": [int(s.block_h) for s in speeds],
