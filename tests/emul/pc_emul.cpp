@@ -397,3 +397,156 @@ extern "C" int pe_simt(void *h, const void *rays_in, uint32_t n, int anyHit, int
     out[6] = rounds; out[7] = n;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Wide (4-ary) collapse of the same tree -- a DESIGN TOOL like pe_simt, not product code and not a test oracle.
+//
+// Every binary inner node i of the derived layout gets a wide record holding the boxes and references of its
+// GRANDCHILDREN (a child that is a leaf is kept as it is): 2 to 4 children, same reference numbering, so instance roots
+// and stack contents need no translation and a walk simply visits every other level.  The boxes tested are the
+// reference's own boxes of those nodes; the skipped intermediate boxes contain them, and the float slab test is monotone
+// in the box bounds, so a child that passes would have passed its parent too: the set of leaves visited -- and with the
+// tie-break key the hit -- is unchanged.  pe_simt_wide runs 32 consecutive rays in lockstep (while-while) through it,
+// counts warp-level and lane-level iterations like pe_simt, and returns the hit records so the claim can be checked
+// against the binary walk bit for bit.
+// out[0..7] = warpWide, laneWide, warpTri, laneTri, warpOther, laneOther, rounds, rays
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct WideNode {
+    float3 bmin[4], bmax[4];
+    uint32_t ref[4];
+    int n;
+};
+std::vector<WideNode> build_wide(const pc_layout::Layout &L) {
+    const size_t inner = L.node64.size() / 4;
+    std::vector<WideNode> W(inner);
+    auto child = [&](size_t node, int side, float3 &mn, float3 &mx, uint32_t &ref) {
+        const pc_layout::Q *q = &L.node64[4 * node];
+        const pc_layout::Q &a = q[side ? 2 : 0], &b = q[side ? 3 : 1];
+        mn = f3(a.x, a.y, a.z);
+        mx = f3(b.x, b.y, b.z);
+        ref = f2u(side ? q[1].w : q[0].w);
+    };
+    for (size_t i = 0; i < inner; i++) {
+        WideNode w{};
+        w.n = 0;
+        for (int side = 0; side < 2; side++) {
+            float3 mn, mx;
+            uint32_t ref;
+            child(i, side, mn, mx, ref);
+            if (!(ref & REF_LEAF)) {  // inner child: take ITS children instead
+                for (int s2 = 0; s2 < 2; s2++) {
+                    child(ref, s2, w.bmin[w.n], w.bmax[w.n], w.ref[w.n]);
+                    w.n++;
+                }
+            } else {
+                w.bmin[w.n] = mn; w.bmax[w.n] = mx; w.ref[w.n] = ref;
+                w.n++;
+            }
+        }
+        W[i] = w;
+    }
+    return W;
+}
+
+struct WideLane {
+    Trav t;
+    bool busy = false;
+    std::vector<uint32_t> stack;
+};
+
+// one wide step of a lane: nearest accepted child next, the others pushed far to near
+template <bool ANY_HIT>
+void wide_step(WideLane &l, const WideNode &w) {
+    Trav &t = l.t;
+    float e[4];
+    int order[4], m = 0;
+    for (int k = 0; k < w.n; k++) {
+        e[k] = slabEntry(w.bmin[k], w.bmax[k], t.o, t.invDir, t.tmaxRay);
+        bool want = e[k] < FLT_MAX;
+        if (!ANY_HIT) want = want && !(e[k] > t.best.wuvt.w * PC_CULL_SLACK);
+        if (want) order[m++] = k;
+    }
+    for (int a = 1; a < m; a++)  // insertion sort by entry distance (stable)
+        for (int b = a; b > 0 && e[order[b]] < e[order[b - 1]]; b--) std::swap(order[b], order[b - 1]);
+    if (m == 0) {
+        if (l.stack.empty()) t.cur = REF_DONE;
+        else { t.cur = l.stack.back(); l.stack.pop_back(); }
+        return;
+    }
+    for (int a = m - 1; a >= 1; a--) l.stack.push_back(w.ref[order[a]]);
+    t.cur = w.ref[order[0]];
+}
+}  // namespace
+
+extern "C" int pe_simt_wide(void *h, const void *rays_in, uint32_t n, int anyHit, double *out, uint32_t *out_flags, void *out_hits) {
+    Emul &e = *(Emul *)h;
+    const DScene &sc = e.sc;
+    const Ray *rays = (const Ray *)rays_in;
+    HitRec *hits = (HitRec *)out_hits;
+    static std::vector<WideNode> W;
+    static const void *builtFor = nullptr;
+    if (builtFor != h) { W = build_wide(e.layout); builtFor = h; }
+    double warpWide = 0, laneWide = 0, warpTri = 0, laneTri = 0, warpOther = 0, laneOther = 0, rounds = 0;
+    TravStats st{0, 0, 0};
+    auto isTri = [](uint32_t c) { return refIsTriLeaf(c); };
+    for (uint32_t base = 0; base < n; base += 32) {
+        std::vector<WideLane> L(32);
+        uint32_t tmpStack[PC_STACK_SIZE];
+        for (uint32_t k = 0; k < 32 && base + k < n; k++) {
+            const Ray &r = rays[base + k];
+            travInit(L[k].t, sc, xyz(r.origin), xyz(r.dir), r.origin.w);
+            L[k].busy = true;
+        }
+        auto finish = [&](uint32_t k, int res) {
+            WideLane &l = L[k];
+            l.busy = false;
+            const int hit = anyHit ? (res == 2 ? 1 : 0) : (l.t.best.wuvt.w < l.t.tmaxRay ? 1 : 0);
+            if (out_flags) out_flags[base + k] = (uint32_t)hit;
+            if (hits) { hits[base + k].wuvt = l.t.best.wuvt; hits[base + k].inst = l.t.best.inst; hits[base + k].tri = l.t.best.tri; hits[base + k].r1 = hits[base + k].r2 = 0; }
+        };
+        for (;;) {
+            int live = 0;
+            for (auto &l : L) live += l.busy;
+            if (!live) break;
+            rounds++;
+            for (;;) {  // phase 1: wide inner steps until every busy lane holds a leaf-type reference
+                int nInner = 0;
+                for (auto &l : L) nInner += l.busy && !(l.t.cur & REF_LEAF);
+                if (!nInner) break;
+                warpWide++;
+                laneWide += nInner;
+                for (auto &l : L)
+                    if (l.busy && !(l.t.cur & REF_LEAF)) {
+                        st.nodes++;
+                        if (anyHit) wide_step<true>(l, W[l.t.cur]); else wide_step<false>(l, W[l.t.cur]);
+                    }
+            }
+            uint32_t maxTri = 0;
+            int nOther = 0;
+            for (uint32_t k = 0; k < 32; k++) {  // phase 2: leaves through the product code's own leaf handlers
+                WideLane &l = L[k];
+                if (!l.busy) continue;
+                if (l.t.cur == REF_DONE) { finish(k, 1); continue; }
+                // hand the lane's stack to travLeaf (it pops the next reference itself)
+                const size_t keep = l.stack.size();
+                l.t.sp = 0;
+                if (keep) { tmpStack[0] = l.stack.back(); l.t.sp = 1; }
+                const uint32_t before = st.tris;
+                const bool tri = isTri(l.t.cur);
+                int r = anyHit ? travLeaf<true, true>(l.t, sc, tmpStack, st) : travLeaf<false, true>(l.t, sc, tmpStack, st);
+                // write back what travLeaf did to the one-entry window: it either popped it (sp == 0) or pushed a marker (sp == 2)
+                if (keep) l.stack.pop_back();
+                for (int q = 0; q < l.t.sp; q++) l.stack.push_back(tmpStack[q]);
+                if (!keep && r == 1 && l.t.sp == 0 && !l.stack.empty()) r = 0;  // (cannot happen: keep == 0 means the stack was empty)
+                if (tri) { const uint32_t done = st.tris - before; laneTri += done; if (done > maxTri) maxTri = done; }
+                else nOther++;
+                if (r) finish(k, r);
+            }
+            warpTri += maxTri;
+            if (nOther) { warpOther++; laneOther += nOther; }
+        }
+    }
+    out[0] = warpWide; out[1] = laneWide; out[2] = warpTri; out[3] = laneTri; out[4] = warpOther; out[5] = laneOther; out[6] = rounds; out[7] = n;
+    return 0;
+}

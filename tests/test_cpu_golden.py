@@ -162,3 +162,30 @@ def test_triangle_pretest_is_conservative():
         assert not (pre & ~ref_reject).any()
         if k < 3:
             assert pre.mean() > 0.3  # and the filter does fire on generic inputs
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_wide_collapse_preserves_hit_records(key):
+    """Design-tool check (tools/wide_bvh_model.py): walking 4-ary nodes that hold every inner node's grandchildren visits
+    the same leaves as the binary walk -- the skipped intermediate boxes contain the tested ones and the float slab test is
+    monotone in the bounds -- so flags, instance / triangle ids and w,u,v,t are identical bit for bit."""
+    import ctypes
+
+    w, h = CONFIGS[key]
+    sc = C.small_scene(key, w, h)
+    rays = C.fixed_rays(sc, w, h, n=2048)
+    emu = C.Emul(sc, w, h)
+    vp = ctypes.c_void_p
+    emu.lib.pe_simt_wide.argtypes = [vp, vp, ctypes.c_uint32, ctypes.c_int, vp, vp, vp]
+    for any_hit in (0, 1):
+        f0, h0, _ = emu.intersect(rays, any_hit)
+        out = np.zeros(8)
+        flags = np.zeros(len(rays), np.uint32)
+        hits = np.zeros(len(rays), _lib.INTERSECTION_DTYPE)
+        emu.lib.pe_simt_wide(emu.h, rays.ctypes.data, len(rays), any_hit, out.ctypes.data, flags.ctypes.data, hits.ctypes.data)
+        assert np.array_equal(flags, f0)
+        if not any_hit:
+            hit = f0 == 1
+            assert hits["wuvt"][hit].tobytes() == h0["wuvt"][hit].tobytes()
+            assert np.array_equal(hits["mesh_instance"][hit], h0["mesh_instance"][hit]) and np.array_equal(hits["tri_index"][hit], h0["tri_index"][hit])
+        assert out[0] > 0 and out[7] == len(rays)
