@@ -92,7 +92,7 @@ struct pc_tracer {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     bool dead = false;
     // scene
-    DevBuf bvh, inst, mats, texData, texMeta, verts, normals, uvs, matIdx, emissives, node64, tri48, inst80;
+    DevBuf bvh, inst, mats, texData, texMeta, verts, normals, uvs, matIdx, emissives, node64, tri48, inst80, node128;
     DScene sc{};
     bool hasScene = false;
     int stackNeed = 0;
@@ -530,7 +530,7 @@ void pc_destroy(pc_tracer *tr) {
         if (tr->stream) cudaStreamSynchronize(tr->stream);
         drop_graph(tr);
         DevBuf *all[] = {&tr->bvh, &tr->inst, &tr->mats, &tr->texData, &tr->texMeta, &tr->verts, &tr->normals, &tr->uvs,
-                         &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->traceAcc, &tr->frameAcc,
+                         &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->node128, &tr->traceAcc, &tr->frameAcc,
                          &tr->frameBuf, &tr->seedsDev, &tr->scratch, &tr->params, &tr->debugBuf};
         release_chain_buffers(tr);
         for (int c = 0; c < MAX_CHAINS; c++) {
@@ -627,6 +627,9 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
                           (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16, /*derive_tris=*/false);
     pc_layout::Layout L = lb.build();
     if (!L.error.empty()) return fail(tr, PC_ERR_BAD_SCENE, "%s", L.error.c_str());
+#ifdef PC_WIDE_BVH
+    pc_layout::Builder::build_wide(L);
+#endif
     if (L.stack_need > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
         return fail(tr, PC_ERR_STACK_DEPTH, "BVH needs a %d-entry traversal stack, the kernels have %d", L.stack_need, PC_STACK_SIZE);
     {   // validate what the shading kernels index with
@@ -649,6 +652,9 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     if ((rc = upload(tr, tr->matIdx, v->material_indices, v->material_indices_bytes))) return rc;
     if ((rc = upload(tr, tr->emissives, v->emissives, v->emissives_bytes))) return rc;
     if ((rc = upload(tr, tr->node64, L.node64.data(), L.node64.size() * 16))) return rc;
+#ifdef PC_WIDE_BVH
+    if ((rc = upload(tr, tr->node128, L.node128.data(), L.node128.size() * 16))) return rc;
+#endif
     {   // tri48 is derived on the device from the vertices and BVH nodes uploaded above
         const size_t nTris = v->vertices_bytes / 48, nNodes = v->bvh_nodes_bytes / 32;
         CU(tr, PC_ERR_ALLOC, tr->tri48.alloc(nTris * 48));
@@ -663,6 +669,9 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaStreamSynchronize(tr->stream));  // host vectors die with this scope
     DScene &s = tr->sc;
     s.node64 = (const float4 *)tr->node64.p;
+#ifdef PC_WIDE_BVH
+    s.node128 = (const float4 *)tr->node128.p;
+#endif
     s.tri48 = (const float4 *)tr->tri48.p;
     s.inst80 = (const float4 *)tr->inst80.p;
     s.rootRef = L.root_ref;

@@ -57,6 +57,7 @@ inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 struct Layout {
     std::vector<Q> node64;  // 4 per inner node
+    std::vector<Q> node128;  // 8 per inner node: the 4-ary collapse (PC_WIDE_BVH builds only), see build_wide()
     std::vector<Q> tri48;   // 3 per triangle
     std::vector<Q> inst80;  // 5 per instance
     uint32_t root_ref = 0;
@@ -131,6 +132,47 @@ class Builder {
         // one restore marker per instance entered
         L.stack_need = L.top_depth + 1 + L.mesh_depth + 1;
         return L;
+    }
+
+    // The 4-ary collapse (experiment, PC_WIDE_BVH): record i holds the boxes and references of binary inner node i's
+    // GRANDCHILDREN (a child that is a leaf is kept as it is) -- 2 to 4 children, same reference numbering as node64, so
+    // instance roots and stack contents need no translation and a walk visits every other level.
+    //   q[2k] = {child k min.xyz, ref k}   q[2k+1] = {child k max.xyz, -}   q[1].w = number of children
+    // The boxes are the reference's own; the skipped intermediate boxes contain them and the float slab test is monotone
+    // in the bounds, so the set of leaves a ray visits -- and with the tie-break key its hit -- is the binary walk's
+    // (tests/test_cpu_golden.py::test_wide_collapse_preserves_hit_records).  A walk pushes up to 3 entries per wide level.
+    static void build_wide(Layout &L) {
+        const size_t inner = L.node64.size() / 4;
+        L.node128.assign(8 * inner, Q{0, 0, 0, 0});
+        auto child = [&](size_t node, int side, Q &mn, Q &mx) {
+            const Q *q = &L.node64[4 * node];
+            mn = q[side ? 2 : 0];
+            mx = q[side ? 3 : 1];
+            mn.w = side ? q[1].w : q[0].w;  // the child's reference
+            mx.w = 0.f;
+        };
+        for (size_t i = 0; i < inner; i++) {
+            Q *w = &L.node128[8 * i];
+            uint32_t n = 0;
+            for (int side = 0; side < 2; side++) {
+                Q mn, mx;
+                child(i, side, mn, mx);
+                uint32_t ref;
+                memcpy(&ref, &mn.w, 4);
+                if (!(ref & REF_LEAF)) {
+                    for (int s2 = 0; s2 < 2; s2++) {
+                        child(ref, s2, w[2 * n], w[2 * n + 1]);
+                        n++;
+                    }
+                } else {
+                    w[2 * n] = mn;
+                    w[2 * n + 1] = mx;
+                    n++;
+                }
+            }
+            w[1].w = u2f(n);
+        }
+        L.stack_need = 3 * ((L.top_depth + 1) / 2) + 1 + 3 * ((L.mesh_depth + 1) / 2) + 1;
     }
 
   private:

@@ -86,8 +86,8 @@ def fixed_rays(sc, w, h, n=4096, seed=7):
 class Emul:
     """tests/emul/libpc_emul.so: the CUDA device functions compiled for the host (TEST ONLY)."""
 
-    def __init__(self, sc, w, h):
-        lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emul", "libpc_emul.so"))
+    def __init__(self, sc, w, h, variant=""):
+        lib = ctypes.CDLL(os.path.join(ROOT, "tests", "emul", f"libpc_emul{variant}.so"))
         lib.pe_create.restype = vp
         lib.pe_create.argtypes = [ctypes.POINTER(_lib.SceneView)]
         lib.pe_destroy.argtypes = [vp]

@@ -45,8 +45,14 @@ void *pe_create(const pc_scene_view *v) {
                          (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16);
     e->layout = b.build();
     e->error = e->layout.error;
+#ifdef PC_WIDE_BVH
+    if (e->error.empty()) pc_layout::Builder::build_wide(e->layout);
+#endif
     DScene &s = e->sc;
     s.node64 = (const float4 *)e->layout.node64.data();
+#ifdef PC_WIDE_BVH
+    s.node128 = (const float4 *)e->layout.node128.data();
+#endif
     s.tri48 = (const float4 *)e->layout.tri48.data();
     s.inst80 = (const float4 *)e->layout.inst80.data();
     s.rootRef = e->layout.root_ref;

@@ -189,3 +189,24 @@ def test_wide_collapse_preserves_hit_records(key):
             assert hits["wuvt"][hit].tobytes() == h0["wuvt"][hit].tobytes()
             assert np.array_equal(hits["mesh_instance"][hit], h0["mesh_instance"][hit]) and np.array_equal(hits["tri_index"][hit], h0["tri_index"][hit])
         assert out[0] > 0 and out[7] == len(rays)
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_wide_traversal_variant_reproduces_the_golden_vectors(key):
+    """PC_WIDE_BVH (the 4-ary traversal experiment, compiled out of the product build): the SAME device code the kernels
+    would run -- pc_layout.hpp build_wide + pc_device.cuh travInnerWide -- built for the host, against the golden hit records
+    and the golden full-depth frame made from the reference's kernels: bit for bit, like the binary walk."""
+    g = load(key)
+    sc, w, h = scene_for(key, g)
+    emu = C.Emul(sc, w, h, variant="_wide")
+    assert emu.layout_info()["stack_need"] <= 64
+    flags, hits, _ = emu.intersect(g["rays"], 0)
+    assert np.array_equal(flags, g["flags"])
+    hit = g["flags"] == 1
+    assert hits["wuvt"][hit].tobytes() == g["hits"]["wuvt"][hit].tobytes()
+    assert np.array_equal(hits["mesh_instance"][hit], g["hits"]["mesh_instance"][hit]) and np.array_equal(hits["tri_index"][hit], g["hits"]["tri_index"][hit])
+    occ_flags, _, _ = emu.intersect(g["occ_rays"], 1)
+    assert np.array_equal(occ_flags, g["occ_flags"])
+    spp, seeds = int(g["spp"]), g["seeds"]
+    emu.trace(T.make_block_request(w, h, spp=spp), seeds)
+    assert C.acc_of(emu, _lib.BUF_TRACE_ACCUMULATOR, w, h).tobytes() == g["full_acc"].tobytes()
