@@ -205,6 +205,22 @@ int pc_merge_rows(pc_tracer *dst, const void *rows, int is_device, const pc_bloc
  * (what a gather sends). */
 int pc_trace_rows(pc_tracer *tr, const pc_block_request *req, void **device_ptr, uint64_t *bytes);
 
+/* ---- one process per GPU (torchrun / MPI style launch): the reference's tracers share ONE OpenCL context so that the
+ * primary's aggregateAccumulator can take a peer device's buffer as its argument (tracer/opencl/device/context.go:11-28,
+ * renderer/default.go:227, resources.go:108-124).  Across processes the same reach is a CUDA IPC mapping:
+ *   worker : pc_ipc_export(slot) once per slot -> 64-byte handle, shipped to the primary's process by any means;
+ *            after each pc_trace, pc_ipc_publish_rows(req, slot) copies the block's rows of the trace accumulator into
+ *            export buffer `slot` (same frame-pixel offsets) and returns when they are visible;
+ *   primary: pc_ipc_open(handle) once -> a device pointer valid in this process (peer access over NVLink);
+ *            pc_merge_rows(primary, (char*)ptr + 16*frame_w*block_y, 1, req) adds the rows with peer loads.
+ * Two slots so that a worker can publish pass i+1 while the primary still reads pass i; the caller orders
+ * publish -> merge -> next publish of the same slot (bench.py does it with the scheduler's stats all-gather). */
+#define PC_IPC_HANDLE_BYTES 64
+int pc_ipc_export(pc_tracer *tr, int slot, void *handle64);
+int pc_ipc_publish_rows(pc_tracer *tr, const pc_block_request *req, int slot);
+int pc_ipc_open(pc_tracer *dst, const void *handle64, void **peer_ptr);
+int pc_ipc_close(pc_tracer *dst, void *peer_ptr);
+
 /* ---- Tracer.SyncFramebuffer (tracer.go:250-276): wait, tonemap (hdr.cl:5-28) rows
  * [0, block_h) and optionally copy the RGBA8 frame (frame_w*frame_h*4 bytes) to rgba_out
  * (what SaveFrameBuffer / CopyFrameBufferToOpenGLTexture read, pipeline.go:216-256). */

@@ -722,6 +722,36 @@ struct TravStats {
 // of t plus the reference-order key -- never by the rounding of the box test.
 #define PC_CULL_SLACK 1.0001f
 
+// Where the traversal stack lives.  The reference keeps 32 uints of private memory per work-item (intersect.cl:4,42,201);
+// a CUDA local array indexed by a run-time stack pointer is the same thing: every push / pop is an LSU round trip through
+// L1 that competes with the node fetches.  PC_SMEM_STACK > 0 keeps the first PC_SMEM_STACK entries of each thread's stack
+// in SHARED memory, one 4-byte column per thread (entry i of thread t at word i * blockDim + t: a warp's accesses to one
+// level hit 32 different banks), and only the rare deeper entries spill to a local array.  The trav* steps below take the
+// stack as a template parameter: a plain uint32_t* (host build, tests, PC_SMEM_STACK == 0) or a SmemStack.
+#ifndef PC_SMEM_STACK
+#define PC_SMEM_STACK 0
+#endif
+PC_HD void stackPush(uint32_t *s, int &sp, uint32_t v) { s[sp++] = v; }
+PC_HD uint32_t stackPop(uint32_t *s, int &sp) { return s[--sp]; }
+#if defined(__CUDACC__)
+template <int DEPTH, int STRIDE>
+struct SmemStack {
+    uint32_t *sm;     // this thread's column of the CTA's shared stack
+    uint32_t *spill;  // PC_STACK_SIZE - DEPTH local entries
+};
+template <int DEPTH, int STRIDE>
+__device__ __forceinline__ void stackPush(SmemStack<DEPTH, STRIDE> s, int &sp, uint32_t v) {
+    if (sp < DEPTH) s.sm[sp * STRIDE] = v;
+    else s.spill[sp - DEPTH] = v;
+    sp++;
+}
+template <int DEPTH, int STRIDE>
+__device__ __forceinline__ uint32_t stackPop(SmemStack<DEPTH, STRIDE> s, int &sp) {
+    --sp;
+    return sp < DEPTH ? s.sm[sp * STRIDE] : s.spill[sp - DEPTH];
+}
+#endif
+
 // Stack-based traversal of the derived layout, written as a per-ray state machine so that the same
 // three steps serve the plain loop below (host build / tests) and the persistent kernels, which
 // interleave them with warp-level refilling of finished lanes (pc_kernels.cuh).
@@ -758,8 +788,8 @@ PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
 
 // One inner-node step: slab-test both children (one aligned 64 B record), descend into the nearer
 // accepted child, push the other.  Requires !(t.cur & REF_LEAF).
-template <bool ANY_HIT, bool COUNT>
-PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+template <bool ANY_HIT, bool COUNT, class Stack>
+PC_HD void travInner(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (COUNT) st.nodes++;
     const float4 *np = sc.node64 + 4 * (size_t)t.cur;
     float4 q0 = PC_LDG(np), q1 = PC_LDG(np + 1), q2 = PC_LDG(np + 2), q3 = PC_LDG(np + 3);
@@ -775,7 +805,7 @@ PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) 
     if (wl && wr) {
         bool leftFirst = tl <= tr;
         const uint32_t farRef = leftFirst ? rref : lref;
-        stack[t.sp++] = farRef;
+        stackPush(stack, t.sp, farRef);
         t.cur = leftFirst ? lref : rref;
 #if defined(__CUDA_ARCH__) && defined(PC_PREFETCH_FAR)
         // the far child is fetched when it is popped, many steps later: ask for its record now (experiment)
@@ -785,7 +815,7 @@ PC_HD void travInner(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) 
     } else if (wl || wr) {
         t.cur = wl ? lref : rref;
     } else {
-        t.cur = t.sp ? stack[--t.sp] : REF_DONE;
+        t.cur = t.sp ? stackPop(stack, t.sp) : REF_DONE;
     }
 }
 
@@ -801,8 +831,8 @@ PC_HD void wideSwap(float &ea, uint32_t &ra, float &eb, uint32_t &rb) {
     const uint32_t r = s ? rb : ra, q = s ? ra : rb;
     ea = e; eb = f; ra = r; rb = q;
 }
-template <bool ANY_HIT, bool COUNT>
-PC_HD void travInnerWide(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+template <bool ANY_HIT, bool COUNT, class Stack>
+PC_HD void travInnerWide(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (COUNT) st.nodes++;
     const float4 *np = sc.node128 + 8 * (size_t)t.cur;
     const float4 q0 = PC_LDG(np), q1 = PC_LDG(np + 1), q2 = PC_LDG(np + 2), q3 = PC_LDG(np + 3);
@@ -826,20 +856,20 @@ PC_HD void travInnerWide(Trav &t, const DScene &sc, uint32_t *stack, TravStats &
     wideSwap(e1, r1, e3, r3);
     wideSwap(e1, r1, e2, r2);  // e0 <= e1 <= e2 <= e3, rejected children (FLT_MAX) last
     if (e0 == FLT_MAX) {
-        t.cur = t.sp ? stack[--t.sp] : REF_DONE;
+        t.cur = t.sp ? stackPop(stack, t.sp) : REF_DONE;
         return;
     }
-    if (e3 < FLT_MAX) stack[t.sp++] = r3;
-    if (e2 < FLT_MAX) stack[t.sp++] = r2;
-    if (e1 < FLT_MAX) stack[t.sp++] = r1;
+    if (e3 < FLT_MAX) stackPush(stack, t.sp, r3);
+    if (e2 < FLT_MAX) stackPush(stack, t.sp, r2);
+    if (e1 < FLT_MAX) stackPush(stack, t.sp, r1);
     t.cur = r0;
 }
 #endif
 
 // Instance entry (:237-249) or the exit marker that restores the world-space ray (:330-335).
 // Returns 0 to continue, 1 when the walk is over.  Requires bits 31:30 == 11 and cur != REF_DONE.
-template <bool COUNT>
-PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+template <bool COUNT, class Stack>
+PC_HD int travOther(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (t.cur == REF_POP_INSTANCE || t.cur == REF_POP_TRANSLATED) {
         t.o = t.o0;
         if (t.cur == REF_POP_INSTANCE) {
@@ -847,7 +877,7 @@ PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
             t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
         }
         if (t.sp == 0) return 1;
-        t.cur = stack[--t.sp];
+        t.cur = stackPop(stack, t.sp);
         return 0;
     }
     if (COUNT) st.instances++;
@@ -862,14 +892,14 @@ PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
         // reciprocals on the way in or out
         float4 m3 = PC_LDG(ip + 4);
         t.o = f3(t.o.x + m3.x, t.o.y + m3.y, t.o.z + m3.z);
-        stack[t.sp++] = REF_POP_TRANSLATED;
+        stackPush(stack, t.sp, REF_POP_TRANSLATED);
     } else if (!(iflags & INST_FLAG_IDENTITY)) {
         // identity matrices are skipped: x*1 + y*0 + z*0 + 0 == x exactly for finite inputs
         float4 m0 = PC_LDG(ip + 1), m1 = PC_LDG(ip + 2), m2 = PC_LDG(ip + 3), m3 = PC_LDG(ip + 4);
         t.o = mul4x1(t.o, m0, m1, m2, m3);
         t.d = mul3x1(t.d, m0, m1, m2);
         t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
-        stack[t.sp++] = REF_POP_INSTANCE;
+        stackPush(stack, t.sp, REF_POP_INSTANCE);
     }
     t.cur = f2u(hdr.x);
     return 0;
@@ -877,8 +907,8 @@ PC_HD int travOther(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
 
 // One triangle leaf (:251-291).  Returns 0 to continue, 1 when the walk is over, 2 when an any-hit
 // ray found its occluder.  Requires refIsTriLeaf(t.cur).
-template <bool ANY_HIT, bool COUNT>
-PC_HD int travTris(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+template <bool ANY_HIT, bool COUNT, class Stack>
+PC_HD int travTris(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     uint32_t tri = t.cur & 0x3FFFFFFFu;
     const float4 *tp = sc.tri48 + 3 * (size_t)tri;
     float4 a = PC_LDG(tp);
@@ -910,13 +940,13 @@ PC_HD int travTris(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
         a = PC_LDG(tp);
     }
     if (t.sp == 0) return 1;
-    t.cur = stack[--t.sp];
+    t.cur = stackPop(stack, t.sp);
     return 0;
 }
 
 // Any leaf-type reference.  Requires t.cur & REF_LEAF.
-template <bool ANY_HIT, bool COUNT>
-PC_HD int travLeaf(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
+template <bool ANY_HIT, bool COUNT, class Stack>
+PC_HD int travLeaf(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (t.cur == REF_DONE) return 1;
     if (refIsTriLeaf(t.cur)) return travTris<ANY_HIT, COUNT>(t, sc, stack, st);
     return travOther<COUNT>(t, sc, stack, st);
@@ -924,9 +954,8 @@ PC_HD int travLeaf(Trav &t, const DScene &sc, uint32_t *stack, TravStats &st) {
 
 // The plain loop: inner-node steps and leaf work in separate loops ("while-while"), so a warp
 // reconverges on "all lanes test boxes" / "all lanes test triangles".  Returns 1 on hit.
-template <bool ANY_HIT, bool COUNT>
-PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &best, TravStats &st) {
-    uint32_t stack[PC_STACK_SIZE];
+template <bool ANY_HIT, bool COUNT, class Stack>
+PC_HD int traverseWith(const DScene &sc, Stack stack, float3 o0, float3 d0, float tmaxRay, Hit &best, TravStats &st) {
     Trav t;
     travInit(t, sc, o0, d0, tmaxRay);
     int r;
@@ -942,6 +971,11 @@ PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &b
     best = t.best;
     if (ANY_HIT) return r == 2 ? 1 : 0;
     return best.wuvt.w < tmaxRay ? 1 : 0;  // (:345)
+}
+template <bool ANY_HIT, bool COUNT>
+PC_HD int traverse(const DScene &sc, float3 o0, float3 d0, float tmaxRay, Hit &best, TravStats &st) {
+    uint32_t stack[PC_STACK_SIZE];
+    return traverseWith<ANY_HIT, COUNT>(sc, &stack[0], o0, d0, tmaxRay, best, st);
 }
 
 // Literal restatement of intersect.cl:184-347 / :26-180 on the reference's own 32 B nodes:

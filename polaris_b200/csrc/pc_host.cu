@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -72,6 +73,13 @@ struct GraphKey {
     }
 };
 
+// An event on the destination's frame stream marking the end of a merge that reads a source tracer's trace
+// accumulator; the source's next Trace waits for it before clearing that accumulator.  Shared: either handle may die first.
+struct ReadFence {
+    cudaEvent_t ev = nullptr;
+    ~ReadFence() { if (ev) cudaEventDestroy(ev); }
+};
+
 constexpr int MAX_CHAINS = 8;
 constexpr int GRAPH_SAMPLES_PER_CHAIN = 4;  // samples each chain contributes to one replay of the captured graph
 struct Chain {
@@ -79,6 +87,10 @@ struct Chain {
     FrameBufs fb{};
     cudaStream_t stream = nullptr;  // chain 0 uses the handle's stream
     cudaEvent_t evJoin = nullptr;
+    // rows [dirtyY0, dirtyY1) of this chain's accumulator (chain 0: the trace accumulator) may be non-zero: the next
+    // pc_trace clears those and its own block instead of the whole frame (the reference clears W*H every Trace,
+    // tracer.go:215; the observable state -- zero outside the traced block -- is the same)
+    uint32_t dirtyY0 = 0, dirtyY1 = 0;
 };
 
 }  // namespace
@@ -106,6 +118,8 @@ struct pc_tracer {
     // stream, and the chains' launches overlap.  Chain 0 accumulates into the trace accumulator, every
     // other chain into its own, added to it once at the end of pc_trace in chain order (deterministic).
     Chain chain[MAX_CHAINS];
+    size_t rayCap = 0;      // rays the per-chain ray / path / hit state holds: sized by the largest BLOCK traced so far
+                            // (+ slack), not by the frame -- at 8 GPUs a rank holds 1/8 of it
     int nChains = 0;        // chains with allocated state
     int lastChain = 0;      // chain that traced the last sample of the last pc_trace (pc_read_buffer)
     size_t statusStride = 0;  // words per bounce
@@ -121,8 +135,22 @@ struct pc_tracer {
     cudaGraphExec_t graphExec = nullptr;
     GraphKey graphKey;
     uint64_t launchesPerSample = 0;
-    // frame state (DESIGN.md "frame accumulator reset")
-    bool frameOpen = false, frameOpenByMerge = false;
+    // frame state (DESIGN.md "frame accumulator reset").  Everything that touches the FRAME accumulator (its
+    // one clear per frame, the merges, the tonemap) runs on frameStream under frameMu, so that other tracers' MergeOutput
+    // calls neither wait for this tracer's own Trace (the reference enqueues them without waiting, resources.go:119) nor
+    // serialise behind it on the device.
+    std::mutex frameMu;
+    cudaStream_t frameStream = nullptr;
+    bool frameOpen = false;           // the frame accumulator was cleared for the frame in progress
+    bool ownFirstPassTraced = false;  // this tracer's own first-pass Trace of the open frame has been issued
+    std::vector<uint8_t> firstPassRows;  // rows already merged in the open frame's first pass (a repeat means: a new frame)
+    // multi-process exchange (pc_ipc_*): two frame-sized export buffers other processes map through CUDA IPC
+    DevBuf exportBuf[2];
+    std::vector<void *> ipcOpened;
+    std::mutex readMu;
+    std::vector<std::shared_ptr<ReadFence>> pendingReads;  // merges (possibly on other devices) still reading traceAcc
+    std::vector<std::shared_ptr<ReadFence>> fencePool;     // this tracer's fences as a merge destination, recycled
+    size_t fenceNext = 0;
     pc_stats stats{};
     uint64_t seedState = 0x501A2150ull;
     int persistentGrid = 0, shadeGrid = 0;
@@ -371,11 +399,30 @@ int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, cons
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// (Re)allocate the per-chain state for the current frame size.
-int ensure_chains(pc_tracer *tr, int want) {
+// (Re)allocate the per-chain state: `want` chains, each able to hold `needRays` rays (the block being traced).
+// Growing re-allocates every chain (new device addresses: the captured graph is dropped); the capacity only grows, with
+// 1/8 slack, so the perfect scheduler nudging row boundaries from pass to pass does not re-allocate.
+int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
     if (want < 1) want = 1;
     if (want > MAX_CHAINS) want = MAX_CHAINS;
     const size_t px = (size_t)tr->W * tr->H;
+    if (needRays > px) needRays = px;
+    if (needRays > tr->rayCap) {
+        CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+        drop_graph(tr);
+        for (int c = 0; c < MAX_CHAINS; c++) {
+            Chain &ch = tr->chain[c];
+            DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.permOcc, &ch.permInd};
+            for (DevBuf *b : all) b->release();
+        }
+        size_t cap = needRays + needRays / 8;
+        cap = (cap + 1023) / 1024 * 1024;
+        tr->rayCap = cap > px ? px : cap;
+        tr->statusStride = tr->rayCap / SHADE_TILE + 2;  // one look-back word per k_shade tile (+ the partial one)
+        want = want > tr->nChains ? want : tr->nChains;
+        tr->nChains = 0;
+    }
+    const size_t cap = tr->rayCap;
     for (int c = tr->nChains; c < want; c++) {
         Chain &ch = tr->chain[c];
         if (c == 0) ch.stream = tr->stream;
@@ -383,19 +430,23 @@ int ensure_chains(pc_tracer *tr, int want) {
             CU(tr, PC_ERR_ALLOC, cudaStreamCreateWithFlags(&ch.stream, cudaStreamNonBlocking));
             CU(tr, PC_ERR_ALLOC, cudaEventCreateWithFlags(&ch.evJoin, cudaEventDisableTiming));
         }
-        for (auto &r : ch.rays) CU(tr, PC_ERR_ALLOC, r.alloc(px * 32));
-        CU(tr, PC_ERR_ALLOC, ch.paths.alloc(px * 32));
-        CU(tr, PC_ERR_ALLOC, ch.hitFlags.alloc(px * 4));
-        CU(tr, PC_ERR_ALLOC, ch.hits.alloc(px * 32));
-        CU(tr, PC_ERR_ALLOC, ch.emSamples.alloc(px * 16));
-        CU(tr, PC_ERR_ALLOC, ch.permOcc.alloc(px * 4));
-        CU(tr, PC_ERR_ALLOC, ch.permInd.alloc(px * 4));
+        for (auto &r : ch.rays) CU(tr, PC_ERR_ALLOC, r.alloc(cap * 32));
+        CU(tr, PC_ERR_ALLOC, ch.paths.alloc(cap * 32));
+        CU(tr, PC_ERR_ALLOC, ch.hitFlags.alloc(cap * 4));
+        CU(tr, PC_ERR_ALLOC, ch.hits.alloc(cap * 32));
+        CU(tr, PC_ERR_ALLOC, ch.emSamples.alloc(cap * 16));
+        CU(tr, PC_ERR_ALLOC, ch.permOcc.alloc(cap * 4));
+        CU(tr, PC_ERR_ALLOC, ch.permInd.alloc(cap * 4));
         CU(tr, PC_ERR_ALLOC, ch.status.alloc(tr->statusStride * MAX_BOUNCES * 8));
         if (!ch.ctl.p) {
             CU(tr, PC_ERR_ALLOC, ch.ctl.alloc(sizeof(TraceCtl)));
             CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.ctl.p, 0, sizeof(TraceCtl), tr->stream));
         }
-        if (c > 0) CU(tr, PC_ERR_ALLOC, ch.acc.alloc(px * 16));
+        if (c > 0 && ch.acc.bytes != px * 16) {  // frame indexed like the trace accumulator; only block rows are ever touched
+            CU(tr, PC_ERR_ALLOC, ch.acc.alloc(px * 16));
+            CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.acc.p, 0, ch.acc.bytes, tr->stream));
+            ch.dirtyY0 = ch.dirtyY1 = 0;
+        }
         for (int i = 0; i < 3; i++) ch.fb.rays[i] = (Ray *)ch.rays[i].p;
         ch.fb.paths = (PathRec *)ch.paths.p;
         ch.fb.hitFlags = (uint32_t *)ch.hitFlags.p;
@@ -406,7 +457,6 @@ int ensure_chains(pc_tracer *tr, int want) {
         ch.fb.traceAcc = (float4 *)(c == 0 ? tr->traceAcc.p : ch.acc.p);
         DevBuf *zero[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status};
         for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
-        if (c > 0) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.acc.p, 0, ch.acc.bytes, tr->stream));
         tr->nChains = c + 1;
     }
     return 0;
@@ -417,8 +467,10 @@ void release_chain_buffers(pc_tracer *tr) {
         Chain &ch = tr->chain[c];
         DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.acc, &ch.permOcc, &ch.permInd};
         for (DevBuf *b : all) b->release();
+        ch.dirtyY0 = ch.dirtyY1 = 0;
     }
     tr->nChains = 0;
+    tr->rayCap = 0;
 }
 
 int upload(pc_tracer *tr, DevBuf &b, const void *src, size_t bytes) {
@@ -427,26 +479,63 @@ int upload(pc_tracer *tr, DevBuf &b, const void *src, size_t bytes) {
     return 0;
 }
 
-int clear_acc(pc_tracer *tr, DevBuf &b) {
-    size_t n = (size_t)tr->W * tr->H;
-    k_clear<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, tr->stream>>>((float4 *)b.p, n);
+// clearAccumulator (accumulator.cl:5-9) over rows [y0, y1) of a frame-indexed accumulator
+int clear_rows(pc_tracer *tr, void *acc, uint32_t y0, uint32_t y1, cudaStream_t s) {
+    if (y1 <= y0) return 0;
+    const size_t n = (size_t)tr->W * (y1 - y0);
+    k_clear<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, s>>>((float4 *)acc + (size_t)tr->W * y0, n);
     CU(tr, PC_ERR_KERNEL, cudaGetLastError());
     return 0;
 }
 
+// ClearTraceAccumulator (tracer.go:215) without touching rows that are zero already: clear what earlier traces left
+// behind and the block about to be traced, remember the new block as the dirty range.
+int clear_for_block(pc_tracer *tr, Chain &ch, void *acc, uint32_t y0, uint32_t y1, cudaStream_t s) {
+    int rc = 0;
+    if (ch.dirtyY1 > ch.dirtyY0 && (ch.dirtyY1 < y0 || ch.dirtyY0 > y1)) {  // disjoint: two clears
+        if ((rc = clear_rows(tr, acc, ch.dirtyY0, ch.dirtyY1, s))) return rc;
+        rc = clear_rows(tr, acc, y0, y1, s);
+    } else {
+        const uint32_t lo = ch.dirtyY1 > ch.dirtyY0 && ch.dirtyY0 < y0 ? ch.dirtyY0 : y0;
+        const uint32_t hi = ch.dirtyY1 > ch.dirtyY0 && ch.dirtyY1 > y1 ? ch.dirtyY1 : y1;
+        rc = clear_rows(tr, acc, lo, hi, s);
+    }
+    ch.dirtyY0 = y0;
+    ch.dirtyY1 = y1;
+    return rc;
+}
+
 bool first_pass(const pc_block_request *r) { return r->accumulated_samples <= r->samples_per_pixel; }
 
-int open_frame_for_merge(pc_tracer *dst, const pc_block_request *req) {
-    // The reference clears the frame accumulator inside each tracer's own Trace, racing with
-    // other workers' MergeOutput into the primary.  Here the first first-pass merge
-    // or the tracer's own first-pass Trace -- whichever arrives first -- does the one clear.
-    if (!dst->frameOpen && first_pass(req)) {
-        int rc = clear_acc(dst, dst->frameAcc);
-        if (rc) return rc;
-        dst->frameOpen = true;
-        dst->frameOpenByMerge = true;
-    }
+// The frame accumulator's one clear per frame.  The reference clears it inside each tracer's own Trace
+// (pipeline.Reset, tracer.go:208-213), racing with the other workers' MergeOutput into the primary; here
+// the first first-pass merge or the tracer's own first-pass Trace -- whichever arrives first -- does it.  Caller holds
+// frameMu.  A frame normally ends at pc_sync_framebuffer; when one did not (a worker failed, the client gave up) the next
+// frame is recognised by a first-pass merge of rows that were merged already, or by a second own first-pass Trace.
+int open_frame(pc_tracer *dst, bool newFrame) {
+    if (dst->frameOpen && !newFrame) return 0;
+    int rc = clear_rows(dst, dst->frameAcc.p, 0, dst->H, dst->frameStream);
+    if (rc) return rc;
+    dst->frameOpen = true;
+    dst->ownFirstPassTraced = false;
+    dst->firstPassRows.assign(dst->H, 0);
     return 0;
+}
+int open_frame_for_merge(pc_tracer *dst, const pc_block_request *req) {
+    if (!first_pass(req)) return 0;
+    bool repeat = false;
+    if (dst->frameOpen && dst->firstPassRows.size() == dst->H)
+        for (uint32_t y = req->block_y; y < req->block_y + req->block_h && y < dst->H; y++) repeat = repeat || dst->firstPassRows[y];
+    int rc = open_frame(dst, repeat);
+    if (rc) return rc;
+    for (uint32_t y = req->block_y; y < req->block_y + req->block_h && y < dst->H; y++) dst->firstPassRows[y] = 1;
+    return 0;
+}
+int open_frame_for_trace(pc_tracer *tr) {  // Trace with AccumulatedSamples == 0
+    std::lock_guard<std::mutex> g(tr->frameMu);
+    int rc = open_frame(tr, tr->ownFirstPassTraced);
+    tr->ownFirstPassTraced = true;
+    return rc;
 }
 
 }  // namespace
@@ -490,6 +579,7 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
         return PC_ERR_NO_DEVICE;
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&tr->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&tr->frameStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&tr->evStart);
     if (e == cudaSuccess) e = cudaEventCreate(&tr->evStop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&tr->evFork, cudaEventDisableTiming);
@@ -528,6 +618,10 @@ void pc_destroy(pc_tracer *tr) {
         std::lock_guard<std::mutex> g(tr->mu);
         cudaSetDevice(tr->device);
         if (tr->stream) cudaStreamSynchronize(tr->stream);
+        if (tr->frameStream) cudaStreamSynchronize(tr->frameStream);
+        for (void *p : tr->ipcOpened) cudaIpcCloseMemHandle(p);
+        tr->ipcOpened.clear();
+        for (auto &e : tr->exportBuf) e.release();
         drop_graph(tr);
         DevBuf *all[] = {&tr->bvh, &tr->inst, &tr->mats, &tr->texData, &tr->texMeta, &tr->verts, &tr->normals, &tr->uvs,
                          &tr->matIdx, &tr->emissives, &tr->node64, &tr->tri48, &tr->inst80, &tr->node128, &tr->traceAcc, &tr->frameAcc,
@@ -544,6 +638,7 @@ void pc_destroy(pc_tracer *tr) {
         if (tr->evStart) cudaEventDestroy(tr->evStart);
         if (tr->evStop) cudaEventDestroy(tr->evStop);
         if (tr->stream) cudaStreamDestroy(tr->stream);
+        if (tr->frameStream) cudaStreamDestroy(tr->frameStream);
     }
     delete tr;
 }
@@ -593,20 +688,24 @@ int pc_resize(pc_tracer *tr, uint32_t w, uint32_t h) {
     }
     if (w == tr->W && h == tr->H) return 0;
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->frameStream));
     drop_graph(tr);
     const size_t px = (size_t)w * h;
     release_chain_buffers(tr);
     CU(tr, PC_ERR_ALLOC, tr->traceAcc.alloc(px * 16));
     CU(tr, PC_ERR_ALLOC, tr->frameAcc.alloc(px * 16));
     CU(tr, PC_ERR_ALLOC, tr->frameBuf.alloc(px * 4));
-    CU(tr, PC_ERR_ALLOC, tr->scratch.alloc(px * 32));
-    tr->statusStride = (px + 31) / 32 + 1;  // one status word per 32-ray tile
     tr->W = w;
     tr->H = h;
     DevBuf *zero[] = {&tr->traceAcc, &tr->frameAcc, &tr->frameBuf};
     for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
-    if ((rc = ensure_chains(tr, 1))) return rc;  // further chains are allocated by the first pc_trace that wants them
-    tr->frameOpen = tr->frameOpenByMerge = false;
+    // the per-chain ray / path / hit state is allocated by the first pc_trace, sized by its block
+    {
+        std::lock_guard<std::mutex> fg(tr->frameMu);
+        tr->frameOpen = tr->ownFirstPassTraced = false;
+        tr->firstPassRows.clear();
+    }
+    for (auto &e : tr->exportBuf) e.release();
     return 0;
 }
 
@@ -621,7 +720,8 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
         v->uvs_bytes * 2 != v->vertices_bytes || v->material_indices_bytes * 12 != v->vertices_bytes || v->emissives_bytes % 80)
         return fail(tr, PC_ERR_BAD_SCENE, "scene buffer sizes are inconsistent with the reference layouts");
     const size_t nMat = v->material_nodes_bytes / 64;
-    if (v->scene_diffuse_mat_index >= (int64_t)nMat) return fail(tr, PC_ERR_BAD_SCENE, "scene diffuse material index out of range");
+    if (v->scene_diffuse_mat_index < -1 || v->scene_diffuse_mat_index >= (int64_t)nMat)
+        return fail(tr, PC_ERR_BAD_SCENE, "scene diffuse material index %d out of range (-1 = none, %zu material nodes)", v->scene_diffuse_mat_index, nMat);
     pc_layout::Builder lb((const pc_layout::RefNode *)v->bvh_nodes, v->bvh_nodes_bytes / 32,
                           (const pc_layout::RefInstance *)v->mesh_instances, v->mesh_instances_bytes / 80,
                           (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16, /*derive_tris=*/false);
@@ -734,12 +834,18 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     }
     tr->cam.texelDims = make_float2(1.0f / (float)req->frame_w, 1.0f / (float)req->frame_h);  // resources.go:130-133
     cudaStream_t s = tr->stream;
-    // pipeline.Reset -> ClearFrameAccumulator when the sample counter was reset (tracer.go:208-213)
-    if (req->accumulated_samples == 0 && !tr->frameOpenByMerge) {
-        if ((rc = clear_acc(tr, tr->frameAcc))) return rc;
+    {   // merges enqueued without waiting (possibly by other devices) may still be reading the trace accumulator
+        std::lock_guard<std::mutex> rg(tr->readMu);
+        for (auto &f : tr->pendingReads) CU(tr, PC_ERR_KERNEL, cudaStreamWaitEvent(s, f->ev, 0));
+        tr->pendingReads.clear();
     }
-    if (req->accumulated_samples == 0) tr->frameOpen = true;
-    if ((rc = clear_acc(tr, tr->traceAcc))) return rc;  // ClearTraceAccumulator (tracer.go:215)
+    // pipeline.Reset -> ClearFrameAccumulator when the sample counter was reset (tracer.go:208-213)
+    if (req->accumulated_samples == 0 && (rc = open_frame_for_trace(tr))) return rc;
+    // ClearTraceAccumulator (tracer.go:215).  With the literal Q4 behaviour (and in the debug stages) emissive hits land at
+    // the block-local path index, i.e. possibly outside the block's rows: those modes clear the whole frame.
+    const bool wholeFrame = !tr->optFixQ4 || dbg;
+    const uint32_t rowsY0 = wholeFrame ? 0u : req->block_y, rowsY1 = wholeFrame ? tr->H : req->block_y + req->block_h;
+    if ((rc = clear_for_block(tr, tr->chain[0], tr->traceAcc.p, rowsY0, rowsY1, s))) return rc;
     if (need * 4 > tr->seedsDev.bytes) CU(tr, PC_ERR_ALLOC, tr->seedsDev.alloc(need * 4 + 4096));
     if (need) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->seedsDev.p, seeds, need * 4, cudaMemcpyHostToDevice, s));
     TraceParams hp;
@@ -750,7 +856,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     int nc = (tr->optTimers || dbg) ? 1 : tr->optChains;
     if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
     if (dbg) CU(tr, PC_ERR_ALLOC, tr->debugBuf.bytes >= (size_t)tr->W * tr->H * 4 + 16 ? cudaSuccess : tr->debugBuf.alloc((size_t)tr->W * tr->H * 4 + 16));
-    if ((rc = ensure_chains(tr, nc))) return rc;
+    if ((rc = ensure_chains(tr, nc, (size_t)req->frame_w * req->block_h))) return rc;
     static const uint32_t kChainIndex[MAX_CHAINS] = {0, 1, 2, 3, 4, 5, 6, 7};
     for (int c = 0; c < nc; c++) {
         // reset the persistent part of the control block, keep the three ray counters
@@ -758,7 +864,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
         CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + offsetof(TraceCtl, nextSample), 0, sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
         if (c > 0) {
             CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl + offsetof(TraceCtl, nextSample), &kChainIndex[c], 4, cudaMemcpyHostToDevice, s));
-            if ((rc = clear_acc(tr, tr->chain[c].acc))) return rc;
+            if ((rc = clear_for_block(tr, tr->chain[c], tr->chain[c].acc.p, rowsY0, rowsY1, s))) return rc;
         }
     }
     uint64_t launches = 2;
@@ -816,10 +922,13 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
                 return fail(tr, PC_ERR_KERNEL, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
         }
-        // chains > 0 accumulated into their own buffers: add them in chain order
-        const size_t px = (size_t)tr->W * tr->H;
-        for (int c = 1; c < nc; c++) {
-            k_merge<<<grid_for(px, 256, tr->prop.multiProcessorCount * 8), 256, 0, s>>>((float4 *)tr->traceAcc.p, (const float4 *)tr->chain[c].acc.p, 0, 0, px);
+        // chains > 0 accumulated into their own buffers: add them in chain order, the block's rows only, one launch
+        if (nc > 1) {
+            ChainAccs ca;
+            ca.n = nc - 1;
+            for (int c = 1; c < nc; c++) ca.src[c - 1] = (const float4 *)tr->chain[c].acc.p;
+            const size_t off = (size_t)tr->W * rowsY0, cnt = (size_t)tr->W * (rowsY1 - rowsY0);
+            k_merge_chains<<<grid_for(cnt, 256, tr->prop.multiProcessorCount * 8), 256, 0, s>>>((float4 *)tr->traceAcc.p, ca, off, cnt);
             launches++;
         }
         tr->lastChain = (int)((spp - 1) % (uint32_t)nc);
@@ -908,12 +1017,31 @@ static int check_block(pc_tracer *tr, const pc_block_request *req) {
     return 0;
 }
 
-// Tracer.MergeOutput -> aggregateAccumulator with global offset FrameW*BlockY (resources.go:108-124)
+// Record "the merge just enqueued on dst's frame stream has read src's rows" and hand the fence to src.
+static int fence_source(pc_tracer *dst, pc_tracer *src) {
+    if (dst->fencePool.size() < 64) {
+        auto f = std::make_shared<ReadFence>();
+        CU(dst, PC_ERR_ALLOC, cudaEventCreateWithFlags(&f->ev, cudaEventDisableTiming));
+        dst->fencePool.push_back(f);
+    }
+    std::shared_ptr<ReadFence> f = dst->fencePool[dst->fenceNext++ % dst->fencePool.size()];
+    CU(dst, PC_ERR_KERNEL, cudaEventRecord(f->ev, dst->frameStream));
+    std::lock_guard<std::mutex> rg(src->readMu);
+    if (src->pendingReads.size() >= 32) src->pendingReads.erase(src->pendingReads.begin());  // a re-recorded fence only waits longer
+    src->pendingReads.push_back(f);
+    return 0;
+}
+
+// Tracer.MergeOutput -> aggregateAccumulator with global offset FrameW*BlockY (resources.go:108-124).
+// Every worker calls this on the primary, concurrently, from its own OS thread (renderer/default.go:188-191, SURVEY
+// Q18): serialised per destination by frameMu -- NOT by the handle's mutex, which the primary's own Trace holds while it
+// waits for the device -- and enqueued on the destination's frame stream without waiting (Exec1DNoWait, resources.go:119).
+// The source's rows are complete (pc_trace is synchronous); when src lives on another GPU the loads cross NVLink.
 int pc_merge_output(pc_tracer *dst, pc_tracer *src, const pc_block_request *req) {
     if (!src) return fail(dst, PC_ERR_UNSUPPORTED_TRACER, "merge failed: unsupported tracer instance");
     int rc = enter(dst);
     if (rc) return rc;
-    std::lock_guard<std::mutex> g(dst->mu);  // workers call this concurrently on the primary
+    std::lock_guard<std::mutex> g(dst->frameMu);
     if ((rc = check_block(dst, req))) return rc;
     if (src->W != dst->W || src->H != dst->H) return fail(dst, PC_ERR_NO_FRAME, "source tracer has different frame dimensions");
     if (src->device != dst->device) {
@@ -926,29 +1054,30 @@ int pc_merge_output(pc_tracer *dst, pc_tracer *src, const pc_block_request *req)
     }
     if ((rc = open_frame_for_merge(dst, req))) return rc;
     const size_t off = (size_t)req->frame_w * req->block_y, n = (size_t)req->block_w * req->block_h;
-    // src finished its Trace before the caller got here (pc_trace is synchronous), so its rows are
-    // complete; the add is ordered on dst's stream and completes at pc_sync_framebuffer.
-    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->stream>>>((float4 *)dst->frameAcc.p, (const float4 *)src->traceAcc.p, off, off, n);
+    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->frameStream>>>((float4 *)dst->frameAcc.p, (const float4 *)src->traceAcc.p, off, off, n);
     CU(dst, PC_ERR_KERNEL, cudaGetLastError());
-    return 0;
+    return fence_source(dst, src);
 }
 
+// The same merge for rows that live outside a pc_tracer of this process: a host buffer, a device buffer, or another
+// process's export buffer mapped with pc_ipc_open (then the loads cross NVLink exactly like pc_merge_output's).
 int pc_merge_rows(pc_tracer *dst, const void *rows, int is_device, const pc_block_request *req) {
     int rc = enter(dst);
     if (rc) return rc;
     if (!rows) return fail(dst, PC_ERR_INVALID_ARGUMENT, "null rows");
-    std::lock_guard<std::mutex> g(dst->mu);
+    std::lock_guard<std::mutex> g(dst->frameMu);
     if ((rc = check_block(dst, req))) return rc;
     if ((rc = open_frame_for_merge(dst, req))) return rc;
     const size_t off = (size_t)req->frame_w * req->block_y, n = (size_t)req->block_w * req->block_h;
     const float4 *src = (const float4 *)rows;
     if (!is_device) {
-        CU(dst, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(dst->scratch.p, rows, n * 16, cudaMemcpyHostToDevice, dst->stream));
+        if (dst->scratch.bytes < n * 16) CU(dst, PC_ERR_ALLOC, dst->scratch.alloc(n * 16));
+        CU(dst, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(dst->scratch.p, rows, n * 16, cudaMemcpyHostToDevice, dst->frameStream));
         src = (const float4 *)dst->scratch.p;
     }
-    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->stream>>>((float4 *)dst->frameAcc.p, src, off, 0, n);
+    k_merge<<<grid_for(n, 256, dst->prop.multiProcessorCount * 8), 256, 0, dst->frameStream>>>((float4 *)dst->frameAcc.p, src, off, 0, n);
     CU(dst, PC_ERR_KERNEL, cudaGetLastError());
-    if (!is_device) CU(dst, PC_ERR_KERNEL, cudaStreamSynchronize(dst->stream));  // scratch is reused
+    if (!is_device) CU(dst, PC_ERR_KERNEL, cudaStreamSynchronize(dst->frameStream));  // scratch is reused
     return 0;
 }
 
@@ -962,20 +1091,91 @@ int pc_trace_rows(pc_tracer *tr, const pc_block_request *req, void **device_ptr,
     return 0;
 }
 
+// ---- one process per GPU: the reference reaches a peer tracer's accumulator through a SHARED OpenCL context
+// (device/context.go:11-28, renderer/default.go:227); across processes the equivalent is a CUDA IPC mapping.
+int pc_ipc_export(pc_tracer *tr, int slot, void *handle64) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    if (slot < 0 || slot > 1 || !handle64) return fail(tr, PC_ERR_INVALID_ARGUMENT, "export slot must be 0 or 1");
+    std::lock_guard<std::mutex> g(tr->mu);
+    if (tr->W == 0) return fail(tr, PC_ERR_NO_FRAME, "no frame dimensions");
+    DevBuf &b = tr->exportBuf[slot];
+    const size_t bytes = (size_t)tr->W * tr->H * 16;
+    if (b.bytes != bytes) {
+        b.release();
+        CU(tr, PC_ERR_ALLOC, b.alloc(bytes));
+        CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b.p, 0, bytes, tr->stream));
+        CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == PC_IPC_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, b.p);
+    if (e != cudaSuccess) return fail(tr, PC_ERR_PEER_ACCESS, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    memcpy(handle64, &h, sizeof(h));
+    return 0;
+}
+
+int pc_ipc_publish_rows(pc_tracer *tr, const pc_block_request *req, int slot) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(tr->mu);
+    if ((rc = check_block(tr, req))) return rc;
+    if (slot < 0 || slot > 1 || !tr->exportBuf[slot].p) return fail(tr, PC_ERR_INVALID_ARGUMENT, "export slot %d was not exported", slot);
+    const size_t off = (size_t)req->frame_w * req->block_y * 16, bytes = (size_t)req->block_w * req->block_h * 16;
+    CU(tr, PC_ERR_KERNEL, cudaMemcpyAsync((char *)tr->exportBuf[slot].p + off, (const char *)tr->traceAcc.p + off, bytes, cudaMemcpyDeviceToDevice, tr->stream));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));  // visible to the importing process once this returns
+    return 0;
+}
+
+int pc_ipc_open(pc_tracer *dst, const void *handle64, void **peer_ptr) {
+    int rc = enter(dst);
+    if (rc) return rc;
+    if (!handle64 || !peer_ptr) return fail(dst, PC_ERR_INVALID_ARGUMENT, "null handle");
+    std::lock_guard<std::mutex> g(dst->mu);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(dst, PC_ERR_PEER_ACCESS, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+    }
+    dst->ipcOpened.push_back(p);
+    *peer_ptr = p;
+    return 0;
+}
+
+int pc_ipc_close(pc_tracer *dst, void *peer_ptr) {
+    int rc = enter(dst);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(dst->mu);
+    for (size_t i = 0; i < dst->ipcOpened.size(); i++)
+        if (dst->ipcOpened[i] == peer_ptr) {
+            CU(dst, PC_ERR_KERNEL, cudaStreamSynchronize(dst->frameStream));
+            cudaIpcCloseMemHandle(peer_ptr);
+            dst->ipcOpened.erase(dst->ipcOpened.begin() + i);
+            return 0;
+        }
+    return fail(dst, PC_ERR_INVALID_ARGUMENT, "pointer was not opened with pc_ipc_open");
+}
+
 // Tracer.SyncFramebuffer (tracer.go:250-276) + TonemapSimpleReinhard (resources.go:344-360)
 int pc_sync_framebuffer(pc_tracer *tr, const pc_block_request *req, uint8_t *rgba_out) {
     int rc = enter(tr);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(tr->mu);
+    std::lock_guard<std::mutex> fg(tr->frameMu);
     if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
     if ((rc = check_block(tr, req))) return rc;
     const size_t n = (size_t)req->frame_w * req->block_h;
     const float sampleWeight = 1.0f / (float)(req->accumulated_samples + req->samples_per_pixel);  // resources.go:347
-    k_tonemap<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, tr->stream>>>((const float4 *)tr->frameAcc.p, (uchar4 *)tr->frameBuf.p, n, sampleWeight, req->exposure);
+    cudaStream_t fs = tr->frameStream;
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));  // WaitForKernels (tracer.go:259)
+    k_tonemap<<<grid_for(n, 256, tr->prop.multiProcessorCount * 8), 256, 0, fs>>>((const float4 *)tr->frameAcc.p, (uchar4 *)tr->frameBuf.p, n, sampleWeight, req->exposure);
     CU(tr, PC_ERR_KERNEL, cudaGetLastError());
-    if (rgba_out) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(rgba_out, tr->frameBuf.p, (size_t)tr->W * tr->H * 4, cudaMemcpyDeviceToHost, tr->stream));
-    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
-    tr->frameOpen = tr->frameOpenByMerge = false;
+    if (rgba_out) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpyAsync(rgba_out, tr->frameBuf.p, (size_t)tr->W * tr->H * 4, cudaMemcpyDeviceToHost, fs));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(fs));
+    tr->frameOpen = tr->ownFirstPassTraced = false;
     return 0;
 }
 
@@ -999,9 +1199,17 @@ int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes) {
         case PC_BUF_RAY_COUNTERS: src = lc.ctl.p; have = 12; break;
         default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown buffer %d", which);
     }
-    if (!src || bytes > have) return fail(tr, PC_ERR_INVALID_ARGUMENT, "buffer %d holds %zu bytes, %llu requested", which, have, (unsigned long long)bytes);
+    // per-sample state is sized by the largest block traced (the reference's is frame sized): what lies beyond it was never
+    // written, so a frame-sized read gets zeros there
+    const bool perSample = which <= PC_BUF_EMISSIVE_SAMPLES;
+    const size_t unit = which == PC_BUF_HIT_FLAGS ? 4 : which == PC_BUF_EMISSIVE_SAMPLES ? 16 : 32;
+    if (!src || (bytes > have && !(perSample && bytes <= (uint64_t)tr->W * tr->H * unit)))
+        return fail(tr, PC_ERR_INVALID_ARGUMENT, "buffer %d holds %zu bytes, %llu requested", which, have, (unsigned long long)bytes);
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
-    CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->frameStream));
+    const size_t take = bytes < have ? (size_t)bytes : have;
+    CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(dst, src, take, cudaMemcpyDeviceToHost));
+    if (bytes > take) memset((char *)dst + take, 0, bytes - take);
     return 0;
 }
 
@@ -1011,6 +1219,7 @@ int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode, ui
     std::lock_guard<std::mutex> g(tr->mu);
     if (!tr->hasScene) return fail(tr, PC_ERR_NO_SCENE_DATA, "no scene data uploaded");
     if ((size_t)n > (size_t)tr->W * tr->H) return fail(tr, PC_ERR_INVALID_ARGUMENT, "%u rays exceed the frame's ray buffer", n);
+    if ((rc = ensure_chains(tr, 1, n))) return rc;
     cudaStream_t s = tr->stream;
     Chain &c0 = tr->chain[0];
     TraceCtl *ctl = (TraceCtl *)c0.ctl.p;

@@ -201,10 +201,23 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
 #endif
 #define PC_QUEUE_BATCH 32u
 
+// The per-thread traversal stack of a kernel: PC_SMEM_STACK entries in shared memory (+ a local spill array for deeper
+// walks), or a plain local array when PC_SMEM_STACK == 0 (see pc_device.cuh above SmemStack).
+#if PC_SMEM_STACK
+#define PC_TRAV_STACK(name)                                                         \
+    __shared__ uint32_t name##_smem[PC_SMEM_STACK * TRAV_BLOCK];                    \
+    uint32_t name##_spill[PC_STACK_SIZE > PC_SMEM_STACK ? PC_STACK_SIZE - PC_SMEM_STACK : 1]; \
+    const SmemStack<PC_SMEM_STACK, TRAV_BLOCK> name{name##_smem + threadIdx.x, name##_spill}
+#else
+#define PC_TRAV_STACK(name)                \
+    uint32_t name##_local[PC_STACK_SIZE];  \
+    uint32_t *const name = name##_local
+#endif
+
 #if !PC_TRACE_REFILL
 // Fixed units: a warp pulls 32 consecutive rays and every lane walks its ray with traverse().
-template <bool ANY_HIT, bool COUNT, class Source, class Sink>
-__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+template <bool ANY_HIT, bool COUNT, class Stack, class Source, class Sink>
+__device__ __forceinline__ void trace_queue(const DScene &sc, Stack stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
                                             const uint32_t *perm = nullptr) {
     UnitClaim claim{0u};
     for (;;) {
@@ -218,15 +231,16 @@ __device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, ui
             float tmax;
             src.load(i, o, d, tmax);
             Trav t;
-            const int hit = traverse<ANY_HIT, COUNT>(sc, o, d, tmax, t.best, st);
+            const int hit = traverseWith<ANY_HIT, COUNT>(sc, stack, o, d, tmax, t.best, st);
             t.tmaxRay = tmax;
             sink.store(i, hit, t);
         }
     }
 }
 #else
-template <bool ANY_HIT, bool COUNT, class Source, class Sink>
-__device__ __forceinline__ void trace_queue(const DScene &sc, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink) {
+template <bool ANY_HIT, bool COUNT, class Stack, class Source, class Sink>
+__device__ __forceinline__ void trace_queue(const DScene &sc, Stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+                                            const uint32_t * = nullptr) {
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = lane_id();
     const unsigned ltMask = (1u << lane) - 1u;
@@ -459,9 +473,10 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(D
     TravStats st{0, 0, 0};
     uint32_t missed = 0;
     if (MODE == 0) {
+        PC_TRAV_STACK(stack);
         PrimarySource src{fb, cam, frameW, blockY, randSeed};
         HitSink<COUNT> sink{fb.hitFlags, fb.hits, 0u};
-        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink);
+        trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], n, st, src, sink);
         missed = sink.missed;
     } else {
         const uint32_t tilesX = (frameW + 7) / 8, tilesY = (blockH + 3) / 4;
@@ -522,9 +537,10 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene
     TravStats st{0, 0, 0};
     uint32_t missed = 0;
     if (!REFERENCE) {
+        PC_TRAV_STACK(stack);
         RaySource src{rays};
         HitSink<COUNT> sink{hitFlags, hits, 0u};
-        trace_queue<false, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
+        trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
         missed = sink.missed;
     } else {
         for (;;) {
@@ -586,8 +602,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
     TravStats st{0, 0, 0};
     OcclusionSink<COUNT> sink{rays, paths, emissiveSamples, acc, hitFlags, 0u};
     if (!REFERENCE) {
+        PC_TRAV_STACK(stack);
         RaySource src{rays};
-        trace_queue<true, COUNT>(sc, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
+        trace_queue<true, COUNT>(sc, stack, &ctl->queueHead[queueSlot], n, st, src, sink, perm);
     } else {
         Trav dummy;
         for (;;) {
@@ -626,6 +643,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
     TravStats st{0, 0, 0};
     uint32_t missed = 0, unocc = 0;
     const Ray *qrays = fb.rays[a], *orays = fb.rays[2];
+    PC_TRAV_STACK(stack);
     UnitClaim claim{0u};
     for (;;) {  // the closest-hit queue first ...
         uint32_t size;
@@ -636,7 +654,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
             const uint32_t i = sorted ? __ldcs(fb.permInd + j) : j;
             const Ray r = ld_ray(qrays + i);
             Hit best;
-            const int hit = traverse<false, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+            const int hit = traverseWith<false, COUNT>(sc, stack, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
             __stcs(fb.hitFlags + i, (uint32_t)hit);
             st_hit(fb.hits + i, best.wuvt, best.inst, best.tri);
             if (COUNT && !hit) missed++;
@@ -652,7 +670,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
             const uint32_t i = sorted ? __ldcs(fb.permOcc + j) : j;
             const Ray r = ld_ray(orays + i);
             Hit best;
-            const int hit = traverse<true, COUNT>(sc, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
+            const int hit = traverseWith<true, COUNT>(sc, stack, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
             if (!hit) {
                 const uint32_t pixel = fb.paths[(uint32_t)r.dir.w].meta.x;  // rayGetPathIndex (util/ray.cl:26-28)
                 const float4 s = __ldcs(fb.emissiveSamples + i);
@@ -1065,6 +1083,23 @@ __global__ void k_merge(float4 *__restrict__ dst, const float4 *__restrict__ src
         float4 d = dst[dstOff + g];
         d.x += s.x; d.y += s.y; d.z += s.z;
         dst[dstOff + g] = d;
+    }
+}
+// the sample chains' accumulators added to the trace accumulator in chain order, ((acc + c1) + c2) + ...: the same
+// float32 sums as one k_merge per chain, in one pass over the block's rows
+struct ChainAccs {
+    const float4 *src[7];
+    int n;
+};
+__global__ void k_merge_chains(float4 *__restrict__ dst, ChainAccs ca, size_t off, size_t n) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += stride) {
+        float4 d = dst[off + g];
+        for (int c = 0; c < ca.n; c++) {
+            const float4 s = __ldcs(ca.src[c] + off + g);
+            d.x += s.x; d.y += s.y; d.z += s.z;
+        }
+        dst[off + g] = d;
     }
 }
 __global__ void k_tonemap(const float4 *acc, uchar4 *fb, size_t n, float sampleWeight, float exposure) {

@@ -286,6 +286,23 @@ class CudaTracer(_HandleTracer):
         self._check(self._lib.pc_trace_rows(self._h, ctypes.byref(block_req), ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
+    # -- one process per GPU: the shared-context reach of device/context.go:11-28 across processes (pc_ipc_*)
+    def ipc_export(self, slot: int) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.pc_ipc_export(self._h, int(slot), buf))
+        return buf.raw
+
+    def ipc_publish_rows(self, block_req, slot: int):
+        self._check(self._lib.pc_ipc_publish_rows(self._h, ctypes.byref(block_req), int(slot)))
+
+    def ipc_open(self, handle: bytes) -> int:
+        p = ctypes.c_void_p()
+        self._check(self._lib.pc_ipc_open(self._h, ctypes.create_string_buffer(handle, 64), ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.pc_ipc_close(self._h, ctypes.c_void_p(ptr)))
+
     def debug_intersect(self, rays, mode):
         rays = np.ascontiguousarray(rays, dtype=_lib.RAY_DTYPE)
         n = rays.shape[0]
