@@ -219,6 +219,12 @@ def run_reference(args):
     else:
         name, w, h, spp_full, cfgno = "c5_cornell_4k", 3840, 2160, 1024, 5
     sc = build_scene(name, w, h)
+    try:  # torchrun exports OMP_NUM_THREADS=1 to its ranks; the reference arm uses every host core
+        from oracle import ref_binding
+        if ref_binding.available():
+            ref_binding.RefTracer.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    except Exception as e:  # pragma: no cover
+        log(f"[bench:reference] could not raise the OpenMP thread count: {e}")
     # bounded sample per step so that warmup+steps finish within a few minutes
     spp = 2 if n == 1 else 1
     rows = h if n == 1 else 540
@@ -268,53 +274,83 @@ def workload_config(n, w, h, spp, config="c2", sc=None):
             "l2": "per-step ray/path state (220 B/px x frame, re-written every bounce) exceeds the 126 MB L2; scene data is L2 resident by design"}
 
 
-def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, use_traffic):
+def measured_profile(config, kernel):
+    """What ncu measured for this kernel class on this config (profiles/traffic.json, written by tools/summarize_ncu.py from
+    `ncu --set full` captures kept under profiles/): DRAM bytes per launch, lanes active, IPC, cache hit rates."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(tp))
+    except Exception:
+        return None
+    ent = t.get(config, {}) if isinstance(t.get(config), dict) else {}
+    return ent.get(kernel)
+
+
+def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, config):
     """A second pass of the same workload in PC_OPT_KERNEL_TIMERS mode (CUDA events around every launch on the tracer's
-    stream, one sample chain) with device counters on: algorithmic bytes of the dominant kernel class / its measured time."""
+    stream, one sample chain) with device counters on.  One untimed warm-up trace, then prof_spp >= 64 samples; a kernel
+    class's time is the MEDIAN over the samples of (sum of that class's launches within the sample), so that a cold first
+    sample or a clock ramp does not move it.  achieved = algorithmic bytes of the dominant class / that time."""
     from polaris_b200 import _lib
     from polaris_b200 import tracer as T
 
     tr.set_option(_lib.OPT_KERNEL_TIMERS, 1)
     tr.set_option(_lib.OPT_COUNTERS, 1)
-    req = T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=prof_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR,
-                               exposure=EXPOSURE)
-    tr.trace(req, seeds[: prof_spp * (1 + NUM_BOUNCES)])
+    per = 1 + NUM_BOUNCES
+    mk = lambda n: T.make_block_request(w, h, block_y=block_y, block_h=block_h, spp=n, num_bounces=NUM_BOUNCES,  # noqa: E731
+                                        min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+    tr.trace(mk(2), seeds[: 2 * per])  # warm-up: clocks, caches, lazily created events
+    tr.trace(mk(prof_spp), seeds[: prof_spp * per])
+    st = tr.stats().device
+    cls, us = tr.kernel_timings()
     tr.set_option(_lib.OPT_KERNEL_TIMERS, 0)
     tr.set_option(_lib.OPT_COUNTERS, 0)
-    st = tr.stats().device
     st["_spp"], st["_background"] = prof_spp, sc.scene_diffuse_mat_index != -1
     by = algorithmic_bytes(st, w * block_h, NUM_BOUNCES)
-    times = {n: st["kernel_time_ns"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
-    counts = {n: st["kernel_count"][i] for i, n in enumerate(_lib.KERNEL_CLASS_NAMES)}
-    total_ns = sum(times.values())
-    if counts.get("k_trace"):
-        # PC_OPT_FUSE_TRACE: the occlusion test and the next bounce's query share a launch, and the device
-        # counters are per trace call, not per launch: report the two traversal classes as one ("k_trace" =
-        # the fused launches + the last bounce's stand-alone k_occlusion)
+    names = _lib.KERNEL_CLASS_NAMES
+    assert len(cls) % prof_spp == 0, (len(cls), prof_spp)
+    lps = len(cls) // prof_spp  # launches per sample, the same class sequence every sample
+    cls2, us2 = cls.reshape(prof_spp, lps), us.reshape(prof_spp, lps).astype(np.float64)
+    assert (cls2 == cls2[0]).all()
+    med_us, mean_us, counts = {}, {}, {}
+    for ci, n in enumerate(names):
+        m = cls2[0] == ci
+        if m.any():
+            per_sample = us2[:, m].sum(axis=1)
+            med_us[n], mean_us[n], counts[n] = float(np.median(per_sample)), float(per_sample.mean()), int(m.sum())
+    if "k_trace" in med_us:
+        # PC_OPT_FUSE_TRACE: the occlusion test and the next bounce's query share a launch, and the device counters are
+        # per trace call, not per launch: report the traversal classes as one ("k_trace" = the fused launches + the last
+        # bounce's stand-alone occlusion launch)
         by["k_trace"] = by.pop("k_query") + by.pop("k_occlusion")
-        times["k_trace"] += times.pop("k_query") + times.pop("k_occlusion")
-        counts["k_trace"] += counts.pop("k_query") + counts.pop("k_occlusion")
-    classes = [k for k in ("k_primary", "k_shade", "k_occlusion", "k_query", "k_trace") if counts.get(k)]
-    dom = max(classes, key=lambda k: times[k])
+        for d in (med_us, mean_us, counts):
+            d["k_trace"] = d["k_trace"] + d.pop("k_query", 0) + d.pop("k_occlusion", 0)
+    classes = [k for k in ("k_primary", "k_shade", "k_occlusion", "k_query", "k_trace") if k in med_us]
+    total = sum(med_us.values())
+    dom = max(classes, key=lambda k: med_us[k])
     peak, peak_src = measured_hbm_peak()
-    kern = {}
-    for k in classes:
-        if counts[k]:
-            kern[k] = {"launches": counts[k], "avg_us": times[k] / counts[k] / 1e3, "share": times[k] / max(1, total_ns),
-                       "alg_GBps": by[k] / max(1, times[k])}
-    log("[bench] kernel classes: " + json.dumps(kern))
-    achieved = by[dom] / max(1, times[dom])  # bytes per ns == GB/s
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and use_traffic:  # the ncu capture was taken on config 2
-        try:
-            traffic = json.load(open(tp)).get(dom)
-        except Exception:
-            traffic = None
+    kern = {k: {"launches_per_sample": counts[k], "avg_us": med_us[k] / counts[k], "mean_avg_us": mean_us[k] / counts[k],
+                "share": med_us[k] / total, "alg_GBps": by[k] / prof_spp / (med_us[k] * 1e3)} for k in classes}
+    log("[bench] kernel classes (median over %d samples): %s" % (prof_spp, json.dumps(kern)))
+    achieved = by[dom] / prof_spp / (med_us[dom] * 1e3)  # bytes per ns == GB/s
+    avg_launch_us = med_us[dom] / counts[dom]
     rays = st["query_rays"] + st["occlusion_rays"]
+    prof = measured_profile(config, dom)
+    measured, traffic = None, None
+    if prof:
+        traffic = prof.get("dram_bytes")
+        measured = dict(prof)
+        if traffic:
+            measured["dram_GBps"] = traffic / (avg_launch_us * 1e3)
+            measured["dram_frac"] = measured["dram_GBps"] / peak
+        if prof.get("l2_bytes"):
+            measured["l2_GBps"] = prof["l2_bytes"] / (avg_launch_us * 1e3)
+        measured["note"] = ("ncu --set full of this kernel class on this config (profiles/); bytes are per launch, rates use the "
+                            "launch time measured HERE.  bound = what the counters show limits the kernel")
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / max(1, counts[dom]),
-            "avg_launch_us": times[dom] / max(1, counts[dom]) / 1e3, "kernels": kern,
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / prof_spp / counts[dom],
+            "avg_launch_us": avg_launch_us, "timing": f"median over {prof_spp} samples after a warm-up trace, CUDA events per launch",
+            "kernels": kern, "measured": measured,
             "rays_per_path": rays / (w * block_h * prof_spp), "nodes_per_ray": st["nodes_tested"] / max(1, rays),
             "tris_per_ray": st["tris_tested"] / max(1, rays)}
 
@@ -392,7 +428,7 @@ def run_cuda_single(args):
     d2h = w * h * 4
 
     # ---- roofline pass: same workload, per-kernel CUDA events + device counters
-    roofline = roofline_pass(tr, sc, w, h, 0, h, min(spp, 32), seeds, use_traffic=args.config == "c2")
+    roofline = roofline_pass(tr, sc, w, h, 0, h, min(spp, 64), seeds, args.config)
     tr.close()
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
@@ -418,6 +454,9 @@ def run_cuda_single(args):
         "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ocl,
     }
+    if ocl and ocl.get("value"):
+        # the same-hardware baseline: the reference's own OpenCL program and launch discipline on this very GPU
+        line["vs_reference_on_gpu"] = {"value": value / ocl["value"], "e2e": line["e2e"]["value"] / ocl["value"]}
     emit(line)
     return 0
 
@@ -435,7 +474,7 @@ def run_cuda_multi(args):
     import torch.distributed as dist
 
     from polaris_b200 import tracer as T
-    from polaris_b200.gather import RowGather, StatsExchange
+    from polaris_b200.gather import IpcRowExchange, RowGather, StatsExchange
     from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -443,6 +482,7 @@ def run_cuda_multi(args):
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, pass_spp, cfgno = 3840, 2160, args.spp or 64, 5
+    frame_passes = max(1, 1024 // pass_spp)  # the 1024-spp job of configs[4]: the frame is tonemapped when it is complete
     sc = build_scene("c5_cornell_4k", w, h) if rank == 0 else None
     objs = [sc]
     dist.broadcast_object_list(objs, src=0)  # every GPU holds the full scene (default.go:70-72)
@@ -457,69 +497,107 @@ def run_cuda_multi(args):
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
     sched = PerfectScheduler()
     speeds = [StaticSpeed(tr.speed()) for _ in range(world)]
-    seeds = T.splitmix_seeds(cfgno + 100 * rank, pass_spp * (1 + NUM_BOUNCES))
-    recv_bufs = [torch.empty(w * h * 4, dtype=torch.float32, device="cuda") if rank == 0 else None for _ in range(2)]
-    acc_samples = 0
-    # The exchange is split phase (polaris_b200/gather.py): pass i's rows travel to rank 0, are added and tonemapped while
-    # pass i+1 is being traced; the scheduler's feedback is read two passes late (it was posted a whole pass earlier, so
-    # reading it never waits for a slower rank).  drain() completes everything in flight: the timed region ends with it.
-    pending_gather = []   # at most one: (RowGather, rows, acc_samples of that pass, e2e)
-    pending_stats = []    # StatsExchange objects, oldest first
-    totals = {"rays": 0.0, "launches": 0.0, "have_stats": False}
+    seed_cache = {}
 
-    def read_stats(keep):
-        while len(pending_stats) > keep:
-            res = pending_stats.pop(0).result()
-            totals["have_stats"] = True
-            for r in range(world):
-                speeds[r].set_stats(int(res[r][0]), float(res[r][1]))
+    def pass_seeds(i):  # every pass of every rank draws its own seeds: 16 passes x 64 spp ARE 1024 different samples
+        k = i % 64
+        if k not in seed_cache:
+            seed_cache[k] = T.splitmix_seeds(cfgno + 100 * rank + 10000 * k, pass_spp * (1 + NUM_BOUNCES))
+        return seed_cache[k]
+
+    for k in range(min(64, args.warmup + 2 * args.steps + 4)):
+        pass_seeds(k)
+    # ---- the exchange step.  Default: CUDA IPC mappings + peer loads in k_merge (polaris_b200/gather.py); --exchange nccl:
+    # grouped send/recv of the rows.  Either way it is split phase: pass i's rows are added on rank 0 while pass i+1 is
+    # traced, and the only collective of the data path is the scheduler's (BlockH, RenderTime) all-gather, which doubles as
+    # the hand-shake: stats(i) is posted by a rank after it published pass i and, on rank 0, after it merged pass i-1.
+    use_ipc = args.exchange == "ipc"
+    xch = IpcRowExchange(tr, rank, world, w) if use_ipc else None
+    recv_bufs = [torch.empty(w * h * 4, dtype=torch.float32, device="cuda") if (rank == 0 and not use_ipc) else None for _ in range(2)]
+    state = {"i": 0, "acc": 0}
+    pending_stats = {}    # pass index -> StatsExchange
+    stats_done = {}       # pass index -> result, kept until the scheduler has used it
+    pending_merge = []    # rank 0, at most one: (pass index, rows, acc_samples before that pass, e2e, RowGather | None)
+    totals = {"rays": 0.0, "launches": 0.0, "device_ns": 0.0, "fed": -1}
+
+    def wait_stats(i):
+        if i in pending_stats:
+            res = pending_stats.pop(i).result()
+            stats_done[i] = res
             totals["rays"] += sum(x[2] for x in res)
             totals["launches"] += sum(x[3] for x in res)
-            totals["device_ns"] = totals.get("device_ns", 0.0) + max(x[4] for x in res)  # CUDA-event time of pc_trace, max over ranks
+            totals["device_ns"] += max(x[4] for x in res)  # CUDA-event time of pc_trace, max over ranks
             if rank == 0 and args.verbose:
-                log(f"[bench] pass: rows {[int(x[0]) for x in res]} trace ms {[round(x[1] * 1e3, 1) for x in res]}")
+                log(f"[bench] pass {i}: rows {[int(x[0]) for x in res]} trace ms {[round(x[1] * 1e3, 1) for x in res]}")
 
-    def finish_gather():
-        if not pending_gather:
+    def feed_scheduler(upto):  # Stats() of every tracer -> the perfect scheduler (scheduler.go:58-72), identical on every rank
+        for i in sorted(k for k in stats_done if k <= upto):
+            res = stats_done.pop(i)
+            if i > totals["fed"]:
+                for r in range(world):
+                    speeds[r].set_stats(int(res[r][0]), float(res[r][1]))
+                totals["fed"] = i
+
+    def finish_merge(last=False):
+        if not pending_merge:
             return
-        rg, rows, acc0, e2e = pending_gather.pop(0)
-        blocks = rg.finish()
+        i, rows, acc0, e2e, rg = pending_merge.pop(0)
+        wait_stats(i)  # every rank has published pass i
         if rank == 0:
-            torch.cuda.current_stream().synchronize()  # the received rows are complete before pc_merge_rows reads them on its own stream
-            for r in range(1, world):
-                rr = T.make_block_request(w, h, block_y=int(sum(rows[:r])), block_h=int(rows[r]), spp=pass_spp,
-                                          accumulated_samples=acc0 + pass_spp)
-                tr.merge_rows(blocks[r].data_ptr(), True, rr)
-            tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc0), want_pixels=e2e)
+            def mk(r, y):
+                return T.make_block_request(w, h, block_y=y, block_h=int(rows[r]), spp=pass_spp, accumulated_samples=acc0 + pass_spp)
+            if use_ipc:
+                xch.merge(rows, i, mk)
+            else:
+                blocks = rg.finish()
+                torch.cuda.current_stream().synchronize()  # the received rows are complete before k_merge reads them on the frame stream
+                y = int(rows[0])
+                for r in range(1, world):
+                    tr.merge_rows(blocks[r].data_ptr(), True, mk(r, y))
+                    y += int(rows[r])
+            if e2e or last or (i + 1) % frame_passes == 0:  # SyncFramebuffer once per frame (default.go:159-161); e2e reads every pass
+                tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE, accumulated_samples=acc0), want_pixels=e2e)
+            else:
+                tr.wait_for_kernels()  # the peers' slots of pass i are free again once this returns (before stats(i+1) is posted)
+        elif rg is not None:
+            rg.finish()
 
     def drain():
-        finish_gather()
-        read_stats(0)
+        finish_merge(last=True)
+        for i in sorted(pending_stats):
+            wait_stats(i)
+        feed_scheduler(state["i"])
 
     def step(e2e=False):
-        nonlocal acc_samples
-        # feedback for the perfect scheduler (scheduler.go:50-80), posted a whole pass ago (the very first one is waited for)
-        read_stats(1 if totals["have_stats"] else 0)
-        rows = sched.schedule(speeds, h)  # identical on every rank: fed by the all-gathered timings
+        i, acc0 = state["i"], state["acc"]
+        feed_scheduler(i - 2)  # timings that every rank is known to hold (they were waited for during pass i-1)
+        rows = sched.schedule(speeds, h)
         by = int(sum(rows[:rank]))
         req = T.make_block_request(w, h, block_y=by, block_h=int(rows[rank]), spp=pass_spp, num_bounces=NUM_BOUNCES,
-                                   min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=acc_samples)
+                                   min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=acc0)
         if e2e:
             tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
             tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
         t0 = time.perf_counter()
-        tr.trace(req, seeds)
+        tr.trace(req, pass_seeds(i))
         t_trace = time.perf_counter() - t0
         d = tr.stats().device
-        finish_gather()  # the previous pass's rows arrived while this one was traced: add + tonemap on rank 0
-        # exchange step of THIS pass: block rows -> rank 0 over NCCL (NVLink); rank 0's own rows go straight into its frame accumulator
-        ptr, nbytes = tr.trace_rows(req)
-        mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
         if rank == 0:
-            tr.merge_output(tr, req)
-        pending_gather.append((RowGather(rows, w, rank, world).start(mine, recv_bufs[(acc_samples // pass_spp) % 2]), rows, acc_samples, e2e))
-        pending_stats.append(StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"], d["device_time_ns"]], world, "cuda"))
-        acc_samples += pass_spp
+            tr.merge_output(tr, req)  # the primary's own rows go straight into its frame accumulator
+        finish_merge()   # pass i-1: arrived / published while this pass was traced (waits for stats(i-1))
+        wait_stats(i - 1)  # ranks != 0: rank 0 posted stats(i-1) after it merged pass i-2 -> slot i % 2 is free
+        rg = None
+        if use_ipc:
+            xch.publish(req, i)
+        else:
+            ptr, nbytes = tr.trace_rows(req)
+            mine = torch.as_tensor(_DevPtr(ptr, nbytes // 4), device="cuda")
+            rg = RowGather(rows, w, rank, world).start(mine, recv_bufs[i % 2])
+            if rank != 0:
+                torch.cuda.current_stream().synchronize()  # the snapshot is taken before the next Trace clears the accumulator
+        pending_merge.append((i, rows, acc0, e2e, rg))
+        pending_stats[i] = StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"], d["device_time_ns"]], world, "cuda")
+        state["i"], state["acc"] = i + 1, acc0 + pass_spp
 
     # the SAME workload on ONE of these GPUs (rank 0 traces the whole frame, the others wait): the N = 1 default of this
     # script is configs[1], a different frame, so the 1-GPU point of the configs[4] scaling curve is measured here
@@ -527,11 +605,11 @@ def run_cuda_multi(args):
     if not args.no_single:
         if rank == 0:
             vals = []
-            for i in range(3):
+            for i in range(4):
                 req1 = T.make_block_request(w, h, spp=pass_spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                tr.trace(req1, seeds)
+                tr.trace(req1, pass_seeds(i))
                 tr.merge_output(tr, req1)
                 tr.sync_framebuffer(T.make_block_request(w, h, spp=pass_spp, exposure=EXPOSURE), want_pixels=False)
                 torch.cuda.synchronize()
@@ -539,7 +617,7 @@ def run_cuda_multi(args):
                 if i:
                     vals.append((d1["query_rays"] + d1["occlusion_rays"]) / (time.perf_counter() - t0) / 1e6)
             one_gpu = {"value": float(np.mean(vals)), "unit": "Mrays/s", "passes": len(vals),
-                       "note": "one 64-spp pass of the whole frame on rank 0's GPU alone, same scene / seeds / kernels, measured in this run"}
+                       "note": "one 64-spp pass of the whole frame on rank 0's GPU alone, same scene / kernels, measured in this run"}
             log(f"[bench] the same workload on one GPU: {one_gpu['value']:.1f} Mrays/s")
         dist.barrier()
     for i in range(args.warmup):
@@ -554,7 +632,7 @@ def run_cuda_multi(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-    drain()  # the last pass's rows are gathered, added and tonemapped inside the timed region
+    drain()  # the last pass's rows are added and the frame is tonemapped inside the timed region
     dist.barrier()
     torch.cuda.synchronize()
     rays, launches, device_ns = totals["rays"], totals["launches"], totals["device_ns"]
@@ -562,7 +640,7 @@ def run_cuda_multi(args):
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.item())
     clk = clocks.stop() if rank == 0 else None
-    # e2e
+    # e2e: scene + camera re-sent from host memory on every rank and the RGBA8 frame read back on rank 0, every pass
     step(e2e=True)
     drain()
     dist.barrier()
@@ -581,9 +659,10 @@ def run_cuda_multi(args):
     roofline = None
     if rank == 0:  # rank 0's own row block of the last assignment, per-kernel CUDA events (the other ranks are done)
         rows_last = [int(sp.block_h) for sp in speeds]
-        roofline = roofline_pass(tr, sc, w, h, 0, max(1, rows_last[0]), min(pass_spp, 16), seeds, use_traffic=False)
+        roofline = roofline_pass(tr, sc, w, h, 0, max(1, rows_last[0]), min(pass_spp, 64), pass_seeds(0), "c5")
         roofline["note"] = f"rank 0's block ({rows_last[0]} rows of {h}) of the last row assignment"
     if rank == 0:
+        seeds_bytes = pass_seeds(0).nbytes
         line = {
             "metric": "Mrays/s (all bounces)", "value": rays / dt / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -591,11 +670,19 @@ def run_cuda_multi(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world, w, h, 1024),
             "spp_mpix_per_s": w * h * pass_spp * args.steps / dt / 1e6, "gpu_launches": int(launches) + 2 * args.steps * world,
             "clocks": clk, "rows_last_step": [int(s.block_h) for s in speeds],
+            "exchange": ("CUDA IPC mappings of the workers' export buffers, k_merge on rank 0 loads the rows over NVLink while adding"
+                         if use_ipc else "NCCL grouped send/recv of the rows + k_merge"),
             "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s",
-                    "h2d_bytes_per_step": int((sc.nbytes() + seeds.nbytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
+                    "h2d_bytes_per_step": int((sc.nbytes() + seeds_bytes + 76) * world), "d2h_bytes_per_step": w * h * 4},
             "roofline": roofline, "cpu_baseline": None, "one_gpu_same_workload": one_gpu,
         }
+        if one_gpu:
+            line["speedup_vs_one_gpu_same_workload"] = {"value": line["value"] / one_gpu["value"], "e2e": line["e2e"]["value"] / one_gpu["value"]}
         emit(line)
+    if xch is not None:
+        tr.wait_for_kernels()
+        dist.barrier()
+        xch.close()
     tr.close()
     dist.destroy_process_group()
     return 0
@@ -633,6 +720,8 @@ def main():
     ap.add_argument("--no-opencl", action="store_true", help="skip the reference-OpenCL-kernels-on-this-GPU baseline")
     ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
     ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")
+    ap.add_argument("--exchange", default="ipc", choices=["ipc", "nccl"],
+                    help="N > 1: how block rows reach rank 0 (ipc: CUDA IPC mappings + peer loads, nccl: grouped send/recv)")
     ap.add_argument("--opt", action="append", default=[], help="NAME=VALUE tracer option, e.g. PRIMARY_PACKETS=0 (experiments)")
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
                     help="N=1 only: BASELINE config to run (default c2 = configs[1], the one the metric is quoted on)")

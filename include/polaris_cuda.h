@@ -191,6 +191,10 @@ int pc_trace(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds,
              size_t n_seeds, pc_stats *stats);
 /* Tracer.Stats (tracer.go:145) for the last pc_trace. */
 int pc_get_stats(pc_tracer *tr, pc_stats *stats);
+/* PC_OPT_KERNEL_TIMERS: the CUDA-event time of EVERY launch of the last pc_trace, in launch order (classes[i] is a
+ * pc_kernel_class, us[i] microseconds); *n receives the number of launches, at most cap entries are copied.  What a
+ * median per kernel class is computed from (the per-class sums of pc_stats include the cold first sample). */
+int pc_get_kernel_timings(pc_tracer *tr, uint32_t *classes, float *us, uint32_t cap, uint32_t *n);
 
 /* ---- Tracer.MergeOutput (tracer.go:279-286): dst.frameAccumulator[rows] += src.traceAccumulator[rows].
  * dst and src may live on different GPUs (peer loads over NVLink). Returns without
@@ -220,6 +224,10 @@ int pc_ipc_export(pc_tracer *tr, int slot, void *handle64);
 int pc_ipc_publish_rows(pc_tracer *tr, const pc_block_request *req, int slot);
 int pc_ipc_open(pc_tracer *dst, const void *handle64, void **peer_ptr);
 int pc_ipc_close(pc_tracer *dst, void *peer_ptr);
+
+/* Device.WaitForKernels (what SyncFramebuffer starts with, tracer.go:259): returns when every launch enqueued on this
+ * handle, merges included, has completed. */
+int pc_wait_for_kernels(pc_tracer *tr);
 
 /* ---- Tracer.SyncFramebuffer (tracer.go:250-276): wait, tonemap (hdr.cl:5-28) rows
  * [0, block_h) and optionally copy the RGBA8 frame (frame_w*frame_h*4 bytes) to rgba_out

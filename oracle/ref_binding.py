@@ -38,6 +38,7 @@ _SYMS = [
     ("pr_debug_tonemap", ctypes.c_int, [vp, u32, f32, f32, vp]),
     ("pr_stack_need", ctypes.c_int, [vp]),
     ("pr_num_threads", ctypes.c_int, []),
+    ("pr_set_num_threads", None, [ctypes.c_int]),
 ]
 _lib_handle = None
 
@@ -94,6 +95,11 @@ class RefTracer(_HandleTracer):
 
     def threads(self):
         return int(load().pr_num_threads())
+
+    @staticmethod
+    def set_threads(n: int):
+        """Use n OpenMP threads from now on (a launcher may have exported OMP_NUM_THREADS=1)."""
+        load().pr_set_num_threads(int(n))
 
     def stack_need(self):
         return int(self._lib.pr_stack_need(self._h))

@@ -116,6 +116,7 @@ SYMBOLS = [
     ("pc_set_option", ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int]),
     ("pc_trace", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, _P(Stats)]),
     ("pc_get_stats", ctypes.c_int, [vp, _P(Stats)]),
+    ("pc_get_kernel_timings", ctypes.c_int, [vp, vp, vp, u32, _P(u32)]),
     ("pc_merge_output", ctypes.c_int, [vp, vp, _P(BlockRequest)]),
     ("pc_merge_rows", ctypes.c_int, [vp, vp, ctypes.c_int, _P(BlockRequest)]),
     ("pc_trace_rows", ctypes.c_int, [vp, _P(BlockRequest), _P(vp), _P(u64)]),
@@ -123,6 +124,7 @@ SYMBOLS = [
     ("pc_ipc_publish_rows", ctypes.c_int, [vp, _P(BlockRequest), ctypes.c_int]),
     ("pc_ipc_open", ctypes.c_int, [vp, vp, _P(vp)]),
     ("pc_ipc_close", ctypes.c_int, [vp, vp]),
+    ("pc_wait_for_kernels", ctypes.c_int, [vp]),
     ("pc_sync_framebuffer", ctypes.c_int, [vp, _P(BlockRequest), vp]),
     ("pc_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),
     ("pc_debug_frame_count", u32, [u32, u32]),

@@ -131,6 +131,7 @@ struct pc_tracer {
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
     std::vector<int> timerClass;
+    std::vector<float> timerUs;  // per launch, same order as timerClass (pc_get_kernel_timings)
     // graph cache
     cudaGraphExec_t graphExec = nullptr;
     GraphKey graphKey;
@@ -963,10 +964,13 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     st.indirect_emitted = hc.stats[ST_IND_EMITTED];
     st.unoccluded = hc.stats[ST_UNOCCLUDED];
     st.missed_query_rays = hc.stats[ST_MISSED];
+    tr->timerUs.clear();
     if (tr->optTimers) {
+        tr->timerUs.assign(tr->timerClass.size(), 0.f);
         for (size_t k = 0; k < tr->timerClass.size(); k++) {
             float kms = 0.f;
             if (cudaEventElapsedTime(&kms, tr->timerEvents[2 * k], tr->timerEvents[2 * k + 1]) == cudaSuccess) {
+                tr->timerUs[k] = kms * 1e3f;
                 st.kernel_time_ns[tr->timerClass[k]] += (uint64_t)((double)kms * 1e6);
                 st.kernel_count[tr->timerClass[k]]++;
             }
@@ -1006,6 +1010,18 @@ int pc_get_stats(pc_tracer *tr, pc_stats *stats) {
     if (!tr || !stats) return PC_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> g(tr->mu);
     *stats = tr->stats;
+    return 0;
+}
+
+int pc_get_kernel_timings(pc_tracer *tr, uint32_t *classes, float *us, uint32_t cap, uint32_t *n) {
+    if (!tr || !n) return PC_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> g(tr->mu);
+    const size_t have = tr->timerUs.size();
+    *n = (uint32_t)have;
+    for (size_t k = 0; k < have && k < cap; k++) {
+        if (classes) classes[k] = (uint32_t)tr->timerClass[k];
+        if (us) us[k] = tr->timerUs[k];
+    }
     return 0;
 }
 
@@ -1157,6 +1173,16 @@ int pc_ipc_close(pc_tracer *dst, void *peer_ptr) {
             return 0;
         }
     return fail(dst, PC_ERR_INVALID_ARGUMENT, "pointer was not opened with pc_ipc_open");
+}
+
+// Device.WaitForKernels (tracer/opencl/device/device.go, called by SyncFramebuffer at tracer.go:259): every launch this
+// handle enqueued -- its own trace stream and the merges on its frame stream -- has completed when this returns.
+int pc_wait_for_kernels(pc_tracer *tr) {
+    int rc = enter(tr);
+    if (rc) return rc;
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->frameStream));
+    return 0;
 }
 
 // Tracer.SyncFramebuffer (tracer.go:250-276) + TonemapSimpleReinhard (resources.go:344-360)

@@ -8,7 +8,14 @@ per GPU the same data movement is a gather of each rank's block rows (16 B per p
 `pc_merge_rows`.  It is a grouped send/recv, not a reduce: outside its own rows a rank's accumulator is
 zero, so an all-reduce would move world_size times more bytes.
 
-Backend agnostic: CUDA tensors over NCCL/NVLink on the B200 box, CPU tensors over gloo in the tests.
+Two transports for that one step:
+  * `IpcRowExchange` (default on the B200 box): every rank exports two frame-sized buffers through CUDA IPC
+    (`pc_ipc_export`), rank 0 maps them once (`pc_ipc_open`); per pass a rank publishes its block rows into slot
+    pass % 2 and rank 0's `k_merge` LOADS them from the peer GPU over NVLink while adding -- the transfer is the add,
+    there is no staging copy and no bulk collective.  This is the reference's shared-context merge
+    (device/context.go:11-28) across process boundaries.
+  * `RowGather`: grouped send/recv of the rows (NCCL on GPUs, gloo in the CPU tests), then `pc_merge_rows`.
+Hand-shakes ride on the scheduler's stats all-gather (`StatsExchange`), the only collective of the data path.
 """
 from __future__ import annotations
 
@@ -37,19 +44,20 @@ class RowGather:
             self.blocks = [mine.reshape(rows[0], w, 4)]
             return self
         if rank != 0:
-            self.works.append(dist.isend(mine.contiguous(), dst=0))
+            self.works = dist.batch_isend_irecv([dist.P2POp(dist.isend, mine.contiguous(), 0)])
             return self
         need = sum(rows[1:]) * w * 4
         if recv is None or recv.numel() < need:
             recv = torch.empty(need, dtype=torch.float32, device=mine.device)
         self._keep = (mine, recv)
-        out, off = [mine.reshape(rows[0], w, 4)], 0
+        out, off, ops = [mine.reshape(rows[0], w, 4)], 0, []
         for r in range(1, world):
             n = rows[r] * w * 4
             view = recv[off:off + n]
-            self.works.append(dist.irecv(view, src=r))
+            ops.append(dist.P2POp(dist.irecv, view, r))
             out.append(view.reshape(rows[r], w, 4))
             off += n
+        self.works = dist.batch_isend_irecv(ops) if ops else []  # one grouped launch instead of world-1 serialised ones
         self.blocks = out
         return self
 
@@ -58,6 +66,44 @@ class RowGather:
             wk.wait()
         self.works = []
         return self.blocks if self.rank == 0 else None
+
+
+class IpcRowExchange:
+    """Block rows -> primary through CUDA IPC mappings of the workers' export buffers (see the module docstring).
+
+    Ordering contract (the caller provides it with `StatsExchange`, see bench.py): rank r may `publish` pass i only after
+    rank 0 finished `merge` of pass i - 2 (same slot), and rank 0 may `merge` pass i only after every rank returned from
+    `publish` of pass i."""
+
+    def __init__(self, tracer, rank: int, world: int, frame_w: int):
+        self.tr, self.rank, self.world, self.w = tracer, rank, world, frame_w
+        handles = [tracer.ipc_export(0), tracer.ipc_export(1)] if rank != 0 else None
+        everyone = [None] * world
+        dist.all_gather_object(everyone, handles)
+        self.peers = {}
+        if rank == 0:
+            for r in range(1, world):
+                self.peers[r] = [tracer.ipc_open(h) for h in everyone[r]]
+
+    def publish(self, block_req, pass_index: int):
+        if self.rank != 0:
+            self.tr.ipc_publish_rows(block_req, pass_index % 2)
+
+    def merge(self, rows, pass_index: int, make_req):
+        """rank 0: add every peer's rows of pass `pass_index`; make_req(r) -> the block request of rank r's block."""
+        if self.rank != 0:
+            return
+        y = int(rows[0])
+        for r in range(1, self.world):
+            if rows[r]:
+                self.tr.merge_rows(self.peers[r][pass_index % 2] + 16 * self.w * y, True, make_req(r, y))
+            y += int(rows[r])
+
+    def close(self):
+        for ptrs in self.peers.values():
+            for p in ptrs:
+                self.tr.ipc_close(p)
+        self.peers = {}
 
 
 def gather_rows_to_primary(mine: torch.Tensor, rows, frame_w: int, rank: int, world: int, recv: torch.Tensor | None = None):

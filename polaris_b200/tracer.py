@@ -286,6 +286,18 @@ class CudaTracer(_HandleTracer):
         self._check(self._lib.pc_trace_rows(self._h, ctypes.byref(block_req), ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
+    def wait_for_kernels(self):
+        self._check(self._lib.pc_wait_for_kernels(self._h))
+
+    def kernel_timings(self):
+        """(classes uint32[n], microseconds float32[n]) of every launch of the last trace (PC_OPT_KERNEL_TIMERS)."""
+        n = ctypes.c_uint32(0)
+        self._check(self._lib.pc_get_kernel_timings(self._h, None, None, 0, ctypes.byref(n)))
+        cls, us = np.zeros(n.value, np.uint32), np.zeros(n.value, np.float32)
+        if n.value:
+            self._check(self._lib.pc_get_kernel_timings(self._h, cls.ctypes.data, us.ctypes.data, n.value, ctypes.byref(n)))
+        return cls, us
+
     # -- one process per GPU: the shared-context reach of device/context.go:11-28 across processes (pc_ipc_*)
     def ipc_export(self, slot: int) -> bytes:
         buf = ctypes.create_string_buffer(64)

@@ -86,14 +86,15 @@ def test_product_never_imports_the_oracle():
                     f"{f} mentions the oracle package"
 
 
-def _build_c_client(tmp_path):
+def _build_c_client(tmp_path, name="render_frame"):
     """gcc -std=c99 against include/polaris_cuda.h + libpolaris_cuda.so: what a cgo binding compiles and links against."""
     import subprocess
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "render_frame")
-    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", "-I", os.path.join(root, "include"), "-o", exe,
-                    os.path.join(root, "tests", "cabi", "render_frame.c"), "-L", os.path.join(root, "polaris_b200"), "-lpolaris_cuda",
+    exe = str(tmp_path / name)
+    extra = ["-D_POSIX_C_SOURCE=200809L", "-pthread"] if name == "render_multi" else []
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O1", *extra, "-I", os.path.join(root, "include"), "-o", exe,
+                    os.path.join(root, "tests", "cabi", name + ".c"), "-L", os.path.join(root, "polaris_b200"), "-lpolaris_cuda",
                     "-Wl,-rpath," + os.path.join(root, "polaris_b200")], check=True)
     return exe
 
@@ -101,6 +102,7 @@ def _build_c_client(tmp_path):
 def test_c99_client_compiles_and_links(tmp_path):
     import subprocess
 
-    exe = _build_c_client(tmp_path)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 2 and "usage" in r.stderr  # no GPU work without arguments
+    for name in ("render_frame", "render_multi"):  # one tracer; the renderer's worker threads (default.go:106-196)
+        exe = _build_c_client(tmp_path, name)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "usage" in r.stderr  # no GPU work without arguments
