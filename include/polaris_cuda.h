@@ -147,10 +147,13 @@ typedef enum pc_option {
     PC_OPT_FUSE_TRACE = 7,      /* 1 (default): a bounce's occlusion test (+ emissive accumulation) and the
                                    next bounce's closest-hit query run as ONE persistent launch;
                                    results are bit-identical to 0 (two launches)              */
-    PC_OPT_SORT_RAYS = 8        /* 1 (default): k_shade also writes, per tile, a permutation of the emitted occlusion /
+    PC_OPT_SORT_RAYS = 8,       /* 1 (default): k_shade also writes, per tile, a permutation of the emitted occlusion /
                                    indirect rays sorted by (origin octant of the scene, direction octant,
                                    dominant axis) and the traversal kernels walk the rays in that order;
                                    the rays, their order in the buffers and every result stay bit-identical */
+    PC_OPT_DEFER_OCCLUSION = 9  /* 1 (default, needs PC_OPT_FUSE_TRACE): a sample's LAST occlusion test (+ emissive accumulation) runs
+                                   inside the next sample's primary-ray launch of the same chain instead of as a launch of its
+                                   own (a pure tail); the last sample's is flushed at the end of pc_trace.  Bit-identical.       */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */
@@ -254,6 +257,43 @@ uint32_t pc_debug_frame_count(uint32_t debug_flags, uint32_t num_bounces);
 int pc_trace_debug(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds,
                    uint32_t debug_flags, uint8_t *frames_out, uint64_t frames_cap_bytes,
                    pc_debug_frame *infos, uint32_t infos_cap, uint32_t *n_frames, pc_stats *stats);
+
+/* ---- scene compilation on the device: the geometry half of asset/compiler/compiler.go:81-231 --
+ * top-level BVH over the instances, one BVH per mesh with the SAH sweep of asset/compiler/bvh/bvh_builder.go:124-224,
+ * triangles re-ordered into leaf order, instance and emissive records -- with the BVH build running as level-synchronous
+ * CUDA kernels (polaris_b200/csrc/pc_bvh_build.cu).  Output: the reference's flat buffers, byte-identical to the host
+ * build of libpolaris_scene.so (same split decisions, ties in iteration order), ready for pc_upload_scene.
+ * The handle owns the buffers until pc_compiled_free. */
+typedef struct pc_raw_mesh {      /* one triangle soup as the wavefront reader leaves it                             */
+    const float *vertices;        /* ntris * 9                                                                         */
+    const float *normals;         /* ntris * 9                                                                         */
+    const float *uvs;             /* ntris * 6                                                                         */
+    const int32_t *material;      /* ntris: index into mat_root / mat_emissive                                         */
+    uint32_t ntris;
+} pc_raw_mesh;
+typedef struct pc_raw_instance {  /* asset/scene/reader/wavefront.go:505-523                                           */
+    uint32_t mesh_index;
+    float inv_transform[16];      /* what compiler.go:191 stores                                                       */
+    float bbox_min[3], bbox_max[3], center[3];
+} pc_raw_instance;
+typedef enum pc_compiled_buffer {
+    PC_CB_BVH_NODES = 0, PC_CB_MESH_INSTANCES = 1, PC_CB_EMISSIVES = 2, PC_CB_VERTICES = 3, PC_CB_NORMALS = 4, PC_CB_UVS = 5,
+    PC_CB_MATERIAL_INDEX = 6
+} pc_compiled_buffer;
+void *pc_compile_geometry(int ordinal, const pc_raw_mesh *meshes, uint32_t n_meshes, const pc_raw_instance *insts,
+                          uint32_t n_insts, const int32_t *mat_root, const int32_t *mat_emissive, uint32_t n_materials,
+                          int32_t env_emissive_node);
+/* bvh.Build alone (bvh_builder.go:124-224) over n volumes given as n x 3 float arrays; out_order receives the item order of
+ * the leaves (leaf.ldata = -(first index into out_order), rdata = count). */
+void *pc_build_bvh(int ordinal, const float *bmin, const float *bmax, const float *center, uint32_t n, int min_leaf_items,
+                   uint32_t *out_order);
+const char *pc_compiled_error(void *compiled);                     /* NULL when the build succeeded */
+int pc_compiled_get(void *compiled, int which, const void **ptr, uint64_t *bytes);
+void pc_compiled_depths(void *compiled, int *top_depth, int *mesh_depth);
+/* seconds: [0] triangle bounds, [1] BVH builds (wall), [2] pre-order flatten, [3] leaf-order gather, [4] total,
+ * [5] the device builder's own share of [1] (uploads + kernels + read-backs); out8 has room for 8 doubles */
+void pc_compiled_timing(void *compiled, double *out8);
+void pc_compiled_free(void *compiled);
 
 /* ---- test / oracle hooks ---- */
 int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes);

@@ -65,7 +65,7 @@ assert ctypes.sizeof(BlockRequest) == 48
 BUF_RAYS0, BUF_RAYS1, BUF_RAYS2, BUF_PATHS, BUF_HIT_FLAGS, BUF_INTERSECTIONS = 0, 1, 2, 3, 4, 5
 BUF_EMISSIVE_SAMPLES, BUF_TRACE_ACCUMULATOR, BUF_FRAME_ACCUMULATOR, BUF_FRAME_BUFFER, BUF_RAY_COUNTERS = 6, 7, 8, 9, 10
 # pc_option
-OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE, OPT_SORT_RAYS = 0, 1, 2, 3, 4, 5, 6, 7, 8
+OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE, OPT_SORT_RAYS, OPT_DEFER_OCCLUSION = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY, K_TRACE = 0, 1, 2, 3, 4, 5
 KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query", "k_trace"]
 # pc_debug_flag == opencl.DebugFlag (tracer/opencl/pipeline.go:17-30)
@@ -129,6 +129,13 @@ SYMBOLS = [
     ("pc_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),
     ("pc_debug_frame_count", u32, [u32, u32]),
     ("pc_trace_debug", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, u32, vp, u64, vp, u32, _P(u32), _P(Stats)]),
+    ("pc_compile_geometry", vp, [ctypes.c_int, vp, u32, vp, u32, vp, vp, u32, ctypes.c_int32]),
+    ("pc_build_bvh", vp, [ctypes.c_int, vp, vp, vp, u32, ctypes.c_int, vp]),
+    ("pc_compiled_error", ctypes.c_char_p, [vp]),
+    ("pc_compiled_get", ctypes.c_int, [vp, ctypes.c_int, _P(vp), _P(u64)]),
+    ("pc_compiled_depths", None, [vp, _P(ctypes.c_int), _P(ctypes.c_int)]),
+    ("pc_compiled_timing", None, [vp, vp]),
+    ("pc_compiled_free", None, [vp]),
     ("pc_debug_intersect", ctypes.c_int, [vp, vp, u32, ctypes.c_int, vp, vp]),
     ("pc_debug_bxdf", ctypes.c_int, [vp, vp, u32, vp]),
     ("pc_debug_rng", ctypes.c_int, [vp, vp, u32, u32, vp]),

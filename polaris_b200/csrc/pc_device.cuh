@@ -729,7 +729,7 @@ struct TravStats {
 // level hit 32 different banks), and only the rare deeper entries spill to a local array.  The trav* steps below take the
 // stack as a template parameter: a plain uint32_t* (host build, tests, PC_SMEM_STACK == 0) or a SmemStack.
 #ifndef PC_SMEM_STACK
-#define PC_SMEM_STACK 0
+#define PC_SMEM_STACK 12
 #endif
 PC_HD void stackPush(uint32_t *s, int &sp, uint32_t v) { s[sp++] = v; }
 PC_HD uint32_t stackPop(uint32_t *s, int &sp) { return s[--sp]; }

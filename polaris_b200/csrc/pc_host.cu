@@ -28,6 +28,9 @@
 #ifndef PC_DEFAULT_FUSE_TRACE
 #define PC_DEFAULT_FUSE_TRACE 1
 #endif
+#ifndef PC_DEFAULT_DEFER_OCC
+#define PC_DEFAULT_DEFER_OCC 1
+#endif
 #include "pc_layout.hpp"
 
 using namespace pc;
@@ -64,12 +67,12 @@ struct DevBuf {
 // boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
     uint32_t nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0, defer = 0;
     DScene scene{};  // the captured launches carry the scene's device pointers and scalars BY VALUE: same struct, same graph
     const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
         return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
-               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
+               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && defer == o.defer && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
     }
 };
 
@@ -126,7 +129,7 @@ struct pc_tracer {
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS, optDeferOcc = PC_DEFAULT_DEFER_OCC;
     int occGrid = 0;
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
@@ -292,6 +295,12 @@ static void debug_stage(pc_tracer *tr, Chain &ch, const pc_block_request &req, D
     debug_dump(tr, s, d, flag, bounce);
 }
 
+// Whether a sample's last occlusion launch is deferred into the next sample's k_primary (see k_primary)
+static bool defer_last_occlusion(const pc_tracer *tr, bool dbg) {
+    return tr->optFuse && tr->optDeferOcc && !tr->optRefOrder && !tr->optPackets && !tr->optTimers && !dbg;
+}
+static int last_occlusion_slot(uint32_t nb) { return 1 + 2 * ((int)nb - 1); }  // == the slot the un-deferred launch uses
+
 template <bool COUNT>
 void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches, DebugSink *dbg) {
     cudaStream_t s = ch.stream;
@@ -304,6 +313,8 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     const TraceParams *params = (const TraceParams *)tr->params.p;
     const FrameBufs &fb = ch.fb;
     uint64_t L = 0;
+    const bool defer = defer_last_occlusion(tr, dbg != nullptr);
+    const int sortedOcc = tr->optSort && !tr->optRefOrder ? 1 : 0;
     size_t statusWords = tr->statusStride * nb;
     {
         LaunchTimer lt(tr, PC_K_BEGIN_SAMPLE);
@@ -315,11 +326,11 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     {
     LaunchTimer lt(tr, PC_K_PRIMARY);
     if (tr->optRefOrder)
-        k_primary<2, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
+        k_primary<2, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot, -1, 0);
     else if (tr->optPackets)
-        k_primary<1, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
+        k_primary<1, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot, -1, 0);
     else
-        k_primary<0, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot);
+        k_primary<0, COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, seeds, params, perSample, slot, defer ? last_occlusion_slot(nb) : -1, sortedOcc);
     }
     L++;
     slot++;
@@ -347,6 +358,7 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
             slot += 2;
             continue;
         }
+        if (defer && bounce + 1 == nb) break;  // the last occlusion test rides in the next sample's k_primary (or the final flush)
         // RayIntersectionTest(2) + AccumulateEmissiveSamples(2) (pipeline.go:160-165)
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
@@ -383,17 +395,30 @@ void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32
 // Enqueue perChain[c] samples on every chain c < nChains: fork the chain streams off the handle's stream,
 // let each chain run its samples back to back, join.  Works identically under stream capture (the fork /
 // join events become graph dependencies and the chains become parallel branches of the graph).
-int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, const uint32_t *perChain, uint64_t *launchesPerSample) {
+int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, const uint32_t *perChain, uint64_t *launchesPerSample,
+                   bool flushOcclusion = false, uint64_t *flushLaunches = nullptr) {
     cudaStream_t s0 = tr->stream;
     if (nChains > 1) {
         if (cudaEventRecord(tr->evFork, s0) != cudaSuccess) return 1;
         for (int c = 1; c < nChains; c++)
-            if (perChain[c] && cudaStreamWaitEvent(tr->chain[c].stream, tr->evFork, 0) != cudaSuccess) return 1;
+            if ((perChain[c] || flushOcclusion) && cudaStreamWaitEvent(tr->chain[c].stream, tr->evFork, 0) != cudaSuccess) return 1;
     }
-    for (int c = 0; c < nChains; c++)
+    for (int c = 0; c < nChains; c++) {
         for (uint32_t k = 0; k < perChain[c]; k++) record_sample(tr, tr->chain[c], req, (uint32_t)nChains, launchesPerSample);
+        if (flushOcclusion) {  // the chain's last sample left its last bounce's occlusion rays behind (see k_primary)
+            Chain &ch = tr->chain[c];
+            const int sorted = tr->optSort && !tr->optRefOrder ? 1 : 0;
+            // its own queue head: the sample's k_primary already pulled from last_occlusion_slot (for the sample before it)
+            const int flushSlot = last_occlusion_slot(req.num_bounces) + 1;
+            if (tr->optCounters)
+                k_occlusion<false, true><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb.traceAcc, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
+            else
+                k_occlusion<false, false><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb.traceAcc, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
+            if (flushLaunches) (*flushLaunches)++;
+        }
+    }
     for (int c = 1; c < nChains; c++) {
-        if (!perChain[c]) continue;
+        if (!perChain[c] && !flushOcclusion) continue;
         if (cudaEventRecord(tr->chain[c].evJoin, tr->chain[c].stream) != cudaSuccess) return 1;
         if (cudaStreamWaitEvent(s0, tr->chain[c].evJoin, 0) != cudaSuccess) return 1;
     }
@@ -669,6 +694,7 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_KERNEL_TIMERS: tr->optTimers = value != 0; break;
         case PC_OPT_FUSE_TRACE: tr->optFuse = value != 0; break;
         case PC_OPT_SORT_RAYS: tr->optSort = value != 0; break;
+        case PC_OPT_DEFER_OCCLUSION: tr->optDeferOcc = value != 0; break;
         case PC_OPT_SAMPLE_CHAINS:
             if (value < 1 || value > MAX_CHAINS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample chains must be in [1, %d]", MAX_CHAINS);
             tr->optChains = value;
@@ -863,6 +889,8 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
         // reset the persistent part of the control block, keep the three ray counters
         char *ctl = (char *)tr->chain[c].ctl.p;
         CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + offsetof(TraceCtl, nextSample), 0, sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
+        // ... except the occlusion-ray counter: the first k_primary of this call must find no rays left over (see k_primary)
+        CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + 2 * sizeof(int), 0, sizeof(int), s));
         if (c > 0) {
             CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl + offsetof(TraceCtl, nextSample), &kChainIndex[c], 4, cudaMemcpyHostToDevice, s));
             if ((rc = clear_for_block(tr, tr->chain[c], tr->chain[c].acc.p, rowsY0, rowsY1, s))) return rc;
@@ -889,7 +917,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
+            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; key.defer = tr->optDeferOcc; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;
@@ -915,10 +943,11 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
             const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc);
             for (; done + perGraph <= spp; done += perGraph) CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
         }
-        if (done < spp) {  // the remainder (or everything, without graphs): same chain assignment, direct launches
+        const bool flush = defer_last_occlusion(tr, dbg != nullptr);
+        if (done < spp || flush) {  // the remainder (or everything, without graphs): same chain assignment, direct launches
             uint32_t perChain[MAX_CHAINS] = {};
             for (uint32_t i = done; i < spp; i++) perChain[i % (uint32_t)nc]++;
-            if (enqueue_chains(tr, *req, nc, perChain, &perSampleLaunches)) {
+            if (enqueue_chains(tr, *req, nc, perChain, &perSampleLaunches, flush, &launches)) {
                 tr->dead = true;
                 return fail(tr, PC_ERR_KERNEL, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }

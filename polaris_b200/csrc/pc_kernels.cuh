@@ -457,10 +457,41 @@ struct PrimarySource {
     }
 };
 
-// MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray
+// rayIntersectionTest over rays[2] + accumulateEmissiveSamples for the unoccluded ones.
+// At most one occlusion ray per path and bounce, so the accumulator update needs no atomic
+// (same argument as the reference, pt_integrator.cl:294-295).  hitFlags may be null.
+template <bool COUNT>
+struct OcclusionSink {
+    const Ray *rays;
+    const PathRec *paths;
+    const float4 *emissiveSamples;
+    float4 *acc;
+    uint32_t *hitFlags;
+    uint32_t unocc;
+    __device__ __forceinline__ void store(uint32_t i, int hit, const Trav &) {
+        if (hitFlags) hitFlags[i] = (uint32_t)hit;
+        if (!hit && acc) {
+            const uint32_t pathIndex = (uint32_t)__ldcs(&rays[i].dir.w);  // rayGetPathIndex (util/ray.cl:26-28)
+            const uint32_t pixel = paths[pathIndex].meta.x;
+            const float4 s = __ldcs(emissiveSamples + i);
+            float4 c = acc[pixel];
+            c.x += s.x; c.y += s.y; c.z += s.z;
+            acc[pixel] = c;
+            if (COUNT) unocc++;
+        }
+    }
+};
+
+// MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray.
+// occSlot >= 0 (MODE 0 only): the launch ALSO drains the any-hit queue the PREVIOUS sample of this chain left behind -- its last
+// bounce's occlusion test + emissive accumulation (pipeline.go:160-165), which nothing in the next sample depends on and
+// which as a launch of its own is a pure tail (ncu: 9 % of the warps active, IPC 0.1).  Every warp first pulls primary
+// units, then occlusion units.  The two halves touch disjoint state, with one benign overlap: pathNew rewrites
+// paths[i].meta.x (the pixel index) with the value the occlusion half reads there -- it is the same for every sample of a
+// block.  The last sample's queue is drained by a stand-alone k_occlusion at the end of pc_trace.
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(DScene sc, FrameBufs fb, TraceCtl *ctl, const uint32_t *seeds,
-                                                       const TraceParams *params, uint32_t seedsPerSample, int queueSlot) {
+                                                       const TraceParams *params, uint32_t seedsPerSample, int queueSlot, int occSlot, int sorted) {
     __shared__ uint2 s_stack[MODE == 1 ? (TRAV_BLOCK / 32) * PC_STACK_SIZE : 1];
     const CameraParams cam = params->cam;
     const uint32_t frameW = params->frameW, blockY = params->blockY, blockH = params->blockH;
@@ -478,6 +509,14 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(D
         HitSink<COUNT> sink{fb.hitFlags, fb.hits, 0u};
         trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], n, st, src, sink);
         missed = sink.missed;
+        if (occSlot >= 0) {
+            const uint32_t nO = (uint32_t)ctl->numRays[2];
+            if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
+            OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, 0u};
+            RaySource osrc{fb.rays[2]};
+            trace_queue<true, COUNT>(sc, stack, &ctl->queueHead[occSlot], nO, st, osrc, osink, sorted ? fb.permOcc : nullptr);
+            if (COUNT) warp_add_stat(ctl, ST_UNOCCLUDED, osink.unocc);
+        }
     } else {
         const uint32_t tilesX = (frameW + 7) / 8, tilesY = (blockH + 3) / 4;
         const uint32_t totalItems = MODE == 1 ? tilesX * tilesY * 32u : n;
@@ -567,31 +606,6 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene
         warp_add_stat(ctl, ST_MISSED, missed);
     }
 }
-
-// rayIntersectionTest over rays[2] + accumulateEmissiveSamples for the unoccluded ones.
-// At most one occlusion ray per path and bounce, so the accumulator update needs no atomic
-// (same argument as the reference, pt_integrator.cl:294-295).  hitFlags may be null.
-template <bool COUNT>
-struct OcclusionSink {
-    const Ray *rays;
-    const PathRec *paths;
-    const float4 *emissiveSamples;
-    float4 *acc;
-    uint32_t *hitFlags;
-    uint32_t unocc;
-    __device__ __forceinline__ void store(uint32_t i, int hit, const Trav &) {
-        if (hitFlags) hitFlags[i] = (uint32_t)hit;
-        if (!hit && acc) {
-            const uint32_t pathIndex = (uint32_t)__ldcs(&rays[i].dir.w);  // rayGetPathIndex (util/ray.cl:26-28)
-            const uint32_t pixel = paths[pathIndex].meta.x;
-            const float4 s = __ldcs(emissiveSamples + i);
-            float4 c = acc[pixel];
-            c.x += s.x; c.y += s.y; c.z += s.z;
-            acc[pixel] = c;
-            if (COUNT) unocc++;
-        }
-    }
-};
 
 template <bool REFERENCE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,

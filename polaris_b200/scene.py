@@ -147,6 +147,7 @@ class Scene:
     camera: Camera | None = None
     top_depth: int = 0
     mesh_depth: int = 0
+    compile_timing: dict | None = None  # seconds per phase of the native geometry compiler (compile_scene)
 
     _SECTIONS = ("bvh_nodes", "mesh_instances", "material_nodes", "texture_data", "texture_metadata",
                  "vertices", "normals", "uvs", "material_index", "emissives")
@@ -232,8 +233,39 @@ def scene_lib():
         lib.ps_get.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_uint64)]
         lib.ps_depths.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
         lib.ps_free.argtypes = [ctypes.c_void_p]
+        lib.ps_timing.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         _scene_lib = lib
     return _scene_lib
+
+
+class _GeometryCompiler:
+    """The two producers of the geometry buffers behind one face: "host" = libpolaris_scene.so (ps_*, OpenMP), "cuda" =
+    libpolaris_cuda.so (pc_compile_geometry / pc_build_bvh: the same compiler with the SAH build on the device,
+    csrc/pc_bvh_build.cu).  Both emit byte-identical buffers."""
+
+    def __init__(self, builder="host", ordinal=0):
+        self.builder, self.ordinal = builder, ordinal
+        if builder == "host":
+            lib = scene_lib()
+            self._compile, self._build = lib.ps_compile, lib.ps_build_bvh
+            self.ps_error, self.ps_get, self.ps_depths, self.ps_free = lib.ps_error, lib.ps_get, lib.ps_depths, lib.ps_free
+            self.ps_timing = lib.ps_timing
+        elif builder == "cuda":
+            from . import _lib as cabi
+            lib = cabi.load()
+            self._compile = lambda *a: lib.pc_compile_geometry(ordinal, *a)
+            self._build = lambda *a: lib.pc_build_bvh(ordinal, *a)
+            self.ps_error, self.ps_get, self.ps_depths, self.ps_free = (lib.pc_compiled_error, lib.pc_compiled_get,
+                                                                        lib.pc_compiled_depths, lib.pc_compiled_free)
+            self.ps_timing = lib.pc_compiled_timing
+        else:
+            raise ValueError(f"unknown scene builder {builder!r}")
+
+    def ps_compile(self, *a):
+        return self._compile(*a)
+
+    def ps_build_bvh(self, *a):
+        return self._build(*a)
 
 
 def _fetch(lib, h, which, dtype, shape=None):
@@ -242,13 +274,13 @@ def _fetch(lib, h, which, dtype, shape=None):
     if n.value == 0:
         a = np.zeros(0, dtype=dtype)
     else:
-        a = np.frombuffer(ctypes.string_at(ptr.value, n.value), dtype=dtype).copy()
+        a = np.ctypeslib.as_array((ctypes.c_ubyte * n.value).from_address(ptr.value)).view(dtype).copy()  # one copy
     return a.reshape(shape) if shape else a
 
 
-def build_bvh(bmin, bmax, center, min_leaf_items):
+def build_bvh(bmin, bmax, center, min_leaf_items, builder="host", ordinal=0):
     """bvh.Build on bare volumes; returns (nodes, leaf-ordered item indices)."""
-    lib = scene_lib()
+    lib = _GeometryCompiler(builder, ordinal)
     bmin = np.ascontiguousarray(bmin, dtype=F)
     bmax = np.ascontiguousarray(bmax, dtype=F)
     center = np.ascontiguousarray(center, dtype=F)
@@ -264,8 +296,8 @@ def build_bvh(bmin, bmax, center, min_leaf_items):
         lib.ps_free(h)
 
 
-def compile_scene(raw: RawScene, aspect: float | None = None) -> Scene:
-    lib = scene_lib()
+def compile_scene(raw: RawScene, aspect: float | None = None, builder: str = "host", ordinal: int = 0) -> Scene:
+    lib = _GeometryCompiler(builder, ordinal)
     # --- createLayeredMaterialTrees (compiler.go:271-310); every listed material is "Used"
     mc = MaterialCompiler(raw.materials, raw.textures)
     names = list(raw.materials.keys())
@@ -296,12 +328,15 @@ def compile_scene(raw: RawScene, aspect: float | None = None) -> Scene:
         keep += [v, n, u, mat]
         meshes[i] = _PsMesh(v.ctypes.data, n.ctypes.data, u.ctypes.data, mat.ctypes.data, v.shape[0])
     insts = (_PsInstance * len(raw.instances))()
+    mesh_boxes = {}  # one min/max pass per MESH, not per instance (1 000 instances share two meshes in config 3)
     for i, inst in enumerate(raw.instances):
         # wavefront.go:505-523: M = S*(R*T); instance AABB = translated mesh AABB corners
         trans = gt.translate4(inst.translation)
         m = gt.mul4(gt.scale4((0, 0, 0)), gt.mul4(gt.ident4(), trans))
         inv = gt.inv4(m)
-        lo, hi = raw.meshes[inst.mesh_index].bbox()
+        if inst.mesh_index not in mesh_boxes:
+            mesh_boxes[inst.mesh_index] = raw.meshes[inst.mesh_index].bbox()
+        lo, hi = mesh_boxes[inst.mesh_index]
         a = gt.mul4x1(trans, np.array([*lo, 1], dtype=F))[:3]
         b = gt.mul4x1(trans, np.array([*hi, 1], dtype=F))[:3]
         bmin, bmax = np.minimum(a, b), np.maximum(a, b)
@@ -319,6 +354,8 @@ def compile_scene(raw: RawScene, aspect: float | None = None) -> Scene:
             raise RuntimeError(err.decode())
         td, md = ctypes.c_int(), ctypes.c_int()
         lib.ps_depths(h, ctypes.byref(td), ctypes.byref(md))
+        tim = (ctypes.c_double * 8)()
+        lib.ps_timing(h, tim)
         tex_meta = np.array(mc.tex_meta, dtype=np.uint32).reshape(-1, 4).view(TEXTURE_META_DTYPE).reshape(-1) \
             if mc.tex_meta else np.zeros(0, dtype=TEXTURE_META_DTYPE)
         sc = Scene(
@@ -337,6 +374,8 @@ def compile_scene(raw: RawScene, aspect: float | None = None) -> Scene:
             top_depth=td.value,
             mesh_depth=md.value,
         )
+        sc.compile_timing = {"builder": builder, "bounds_s": tim[0], "bvh_build_s": tim[1], "flatten_s": tim[2], "gather_s": tim[3],
+                             "native_total_s": tim[4], "bvh_build_device_s": tim[5]}
     finally:
         lib.ps_free(h)
     # --- setupCamera (compiler.go:234-241) + cmd/render.go:58

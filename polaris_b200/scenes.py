@@ -18,6 +18,8 @@ to the compiler -- and compiled with `compile_scene`.  Rules taken from the surv
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from .material import TEX_LUMINANCE32F, TEX_RGBA8, TEX_RGBA32F
@@ -334,11 +336,39 @@ def c4_terrain(n=2237, tex=2048, sky=(4096, 2048), seed=1):
 
 
 # ------------------------------------------------------------------------------ front door
-def build(name: str, frame_w=None, frame_h=None, **sizes):
-    """Compile one config; returns (Scene, frame_w, frame_h, spp)."""
+_GENERATORS = {"c1_sphere": "c1_sphere", "c2_cornell": "c2_cornell", "c3_instancing": "c3_instancing",
+               "c4_terrain": "c4_terrain", "c5_cornell_4k": "c2_cornell"}
+_raw_cache = {}
+
+
+def raw_scene(name: str, **sizes):
+    """The procedural RawScene of a config (what the wavefront reader would hand the compiler), memoised: the 10 M-triangle
+    terrain takes most of a minute to generate and several callers (host build, device build, tests) want the same one."""
+    key = (name, tuple(sorted((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in sizes.items())))
+    if key not in _raw_cache:
+        if len(_raw_cache) >= 2:
+            _raw_cache.pop(next(iter(_raw_cache)))
+        _raw_cache[key] = globals()[_GENERATORS[name]](**sizes)
+    return _raw_cache[key]
+
+
+def build(name: str, frame_w=None, frame_h=None, builder: str = "host", **sizes):
+    """Compile one config; returns (Scene, frame_w, frame_h, spp).  builder: "host" (libpolaris_scene.so) or "cuda" (the
+    device BVH build of libpolaris_cuda.so) -- same bytes either way."""
     w, h, spp = CONFIGS[name]
     w, h = frame_w or w, frame_h or h
-    gen = {"c1_sphere": c1_sphere, "c2_cornell": c2_cornell, "c3_instancing": c3_instancing,
-           "c4_terrain": c4_terrain, "c5_cornell_4k": c2_cornell}[name]
-    sc = compile_scene(gen(**sizes), aspect=F(w) / F(h))
+    # POLARIS_SCENE_CACHE=<dir>: keep the compiled scene as a PLRSCN2 dump (the 10 M-triangle terrain takes a minute of
+    # procedural generation + compilation; several bench / profiler runs inside one session share it)
+    cache = os.environ.get("POLARIS_SCENE_CACHE")
+    path = os.path.join(cache, f"{name}_{w}x{h}.plrscn") if cache and not sizes else None
+    if path and os.path.exists(path):
+        from .scene import Scene
+        sc = Scene.load(path)
+        sc.camera.setup_projection(F(w) / F(h))
+        return sc, w, h, spp
+    sc = compile_scene(raw_scene(name, **sizes), aspect=F(w) / F(h), builder=builder)
+    if path:
+        os.makedirs(cache, exist_ok=True)
+        sc.save(path + ".tmp")
+        os.replace(path + ".tmp", path)
     return sc, w, h, spp

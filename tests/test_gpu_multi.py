@@ -31,19 +31,22 @@ def _cam_args(sc):
 
 
 def _replay(sc, w, h, spp, rows_per_frame, ordinal=0):
-    """The same block requests, frame by frame, tracer by tracer, on ONE handle."""
-    cu = C.cuda_for(sc, w, h, ordinal=ordinal)
+    """The same block requests, frame by frame, tracer by tracer, SEQUENTIALLY: one handle traces every block, a second one
+    only receives the merges (a tracer that traced two first-pass blocks of one frame would reset its own frame
+    accumulator in between, like the reference's Trace does: tracer.go:208-213)."""
+    cu, primary = C.cuda_for(sc, w, h, ordinal=ordinal), C.cuda_for(sc, w, h, ordinal=ordinal)
     for fr, rows in enumerate(rows_per_frame):
         y = 0
         for i, bh in enumerate(rows):
             req = T.make_block_request(w, h, block_y=y, block_h=int(bh), spp=spp, accumulated_samples=fr * spp)
             cu.trace(req, T.splitmix_seeds(7 + 100 * i + fr, spp * 6))
-            cu.merge_output(cu, req)
+            primary.merge_output(cu, req)
             y += int(bh)
-        cu.sync_framebuffer(T.make_block_request(w, h, spp=spp, accumulated_samples=fr * spp), want_pixels=fr + 1 == len(rows_per_frame))
-    acc = cu.read_buffer(_lib.BUF_FRAME_ACCUMULATOR, w * h * 4, np.float32)
-    rgba = cu.frame_buffer.copy()
+        primary.sync_framebuffer(T.make_block_request(w, h, spp=spp, accumulated_samples=fr * spp), want_pixels=fr + 1 == len(rows_per_frame))
+    acc = primary.read_buffer(_lib.BUF_FRAME_ACCUMULATOR, w * h * 4, np.float32)
+    rgba = primary.frame_buffer.copy()
     cu.close()
+    primary.close()
     return acc, rgba
 
 

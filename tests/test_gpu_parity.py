@@ -160,7 +160,8 @@ def test_variants_bit_identical():
     ref = None
     for opts in ({}, {"primary_packets": 0}, {"use_graph": 0}, {"counters": 1}, {"reference_order": 1}, {"fuse_trace": 0},
                  {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}, {"sort_rays": 1},
-                 {"sort_rays": 0}, {"sort_rays": 1, "fuse_trace": 0}, {"sort_rays": 1, "counters": 1, "use_graph": 0}):
+                 {"sort_rays": 0}, {"sort_rays": 1, "fuse_trace": 0}, {"sort_rays": 1, "counters": 1, "use_graph": 0},
+                 {"defer_occlusion": 0}, {"defer_occlusion": 0, "use_graph": 0}, {"defer_occlusion": 1, "counters": 1}):
         cu = C.cuda_for(sc, w, h, **opts)
         cu.trace(T.make_block_request(w, h, spp=2), seeds)
         acc = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
@@ -169,6 +170,29 @@ def test_variants_bit_identical():
         if ref is None:
             ref = (acc, cnt)
         assert (acc, cnt) == ref, f"variant {opts} differs"
+
+
+def test_deferred_occlusion_bit_identical_over_many_samples():
+    """PC_OPT_DEFER_OCCLUSION moves a sample's last occlusion test into the next sample's primary launch (graph replays,
+    the direct-launch remainder and the final flush all take part at 22 spp): accumulator, ray totals and the last sample's
+    counters are bit-identical to the plain launch sequence, for 1 and 4 chains."""
+    w, h, spp = 128, 96, 22
+    sc = C.small_scene("c2", w, h)
+    seeds = T.splitmix_seeds(12, spp * 6)
+    for chains in (1, 4):
+        res = []
+        for defer in (1, 0):
+            cu = C.cuda_for(sc, w, h, sample_chains=chains, defer_occlusion=defer)
+            cu.trace(T.make_block_request(w, h, block_y=8, block_h=80, spp=spp), seeds)
+            st = cu.stats().device
+            res.append((cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes(),
+                        cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32).tobytes(), st["query_rays"], st["occlusion_rays"]))
+            if defer:
+                launches = st["kernel_launches"]
+            else:
+                assert st["kernel_launches"] > launches  # one launch per sample saved, one flush per chain added
+            cu.close()
+        assert res[0] == res[1], f"{chains} chains: deferring the last occlusion launch changed the result"
 
 
 def test_sample_chains_equivalent():

@@ -1,13 +1,19 @@
 #!/bin/bash
-# Run under gpurun (ONE GPU): launch list + one `ncu --set full` capture per hot kernel class of the default
-# bench command (config 2).  Outputs land in gpurun_out/; tools/summarize_ncu.py turns them into profiles/*.
+# Run under gpurun (ONE GPU): launch list + one `ncu --set full` capture per hot kernel class of a bench command.
+#   tools/profile_gpu.sh <tag> [config=c2] [spp=4]
+# Outputs land in gpurun_out/ (launches_<tag>_<config>.csv, prof_<kernel>_<tag>_<config>.ncu-rep);
+# tools/summarize_ncu.py <tag> <config> turns them into profiles/*.  Numbers printed by bench.py under ncu are never bench values.
 set -u
 mkdir -p gpurun_out
-R=${1:-r01}
-CMD="python bench.py --steps 1 --warmup 1 --spp 4 --no-cpu --chains 1"
+R=${1:-r02}
+C=${2:-c2}
+SPP=${3:-4}
+export POLARIS_SCENE_CACHE=${POLARIS_SCENE_CACHE:-/tmp/polaris_scenes}
+CMD="python bench.py --config $C --steps 1 --warmup 1 --spp $SPP --no-cpu --chains 1"
 # every launch with its device time (cold-cache, serialised: compare shares, not absolutes)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}.csv $CMD > gpurun_out/launches_${R}.out 2>&1
-for K in k_shade k_trace k_occlusion k_primary; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 2 -f -o gpurun_out/prof_${K}_${R} $CMD > gpurun_out/prof_${K}_${R}.out 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}_${C}.csv $CMD > gpurun_out/launches_${R}_${C}.out 2>&1
+for K in k_trace k_shade k_primary; do
+  # skip the first sample's launches (cold), capture two launches of the class
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 2 -f -o gpurun_out/prof_${K}_${R}_${C} $CMD > gpurun_out/prof_${K}_${R}_${C}.out 2>&1
 done
-ls -la gpurun_out
+ls -la gpurun_out | grep "${R}_${C}"
