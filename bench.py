@@ -431,6 +431,36 @@ def run_cuda_single(args):
     roofline = roofline_pass(tr, sc, w, h, 0, h, min(spp, 64), seeds, args.config)
     tr.close()
 
+    # ---- cold start: raw triangles -> compiled scene ON THE DEVICE (pc_compile_geometry: the reference's SAH build as CUDA
+    # kernels) -> upload -> first frame, on a fresh tracer.  Not part of `value` / `e2e`.
+    cold = None
+    if args.cold_scene or (cfg_name, ()) in scenes._raw_cache:
+        try:
+            from polaris_b200.scene import compile_scene
+            raw = scenes.raw_scene(cfg_name)
+            compile_scene(raw, aspect=np.float32(w) / np.float32(h), builder="cuda")  # CUDA context + first-use allocations
+            t0 = time.perf_counter()
+            sc2 = compile_scene(raw, aspect=np.float32(w) / np.float32(h), builder="cuda")
+            t1 = time.perf_counter()
+            tr2 = T.CudaTracer("cuda:0", 0)
+            tr2.init()
+            tr2.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
+            tr2.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc2)
+            tr2.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc2.camera)
+            req = T.make_block_request(w, h, spp=spp, num_bounces=NUM_BOUNCES, min_bounces_for_rr=MIN_RR, exposure=EXPOSURE)
+            tr2.trace(req, seeds)
+            tr2.merge_output(tr2, req)
+            tr2.sync_framebuffer(T.make_block_request(w, h, spp=spp, exposure=EXPOSURE), want_pixels=True)
+            t2 = time.perf_counter()
+            tr2.close()
+            same = all(getattr(sc, k).tobytes() == getattr(sc2, k).tobytes() for k in sc._SECTIONS)
+            cold = {"compile_scene_s": t1 - t0, "upload_and_first_frame_s": t2 - t1, "total_s": t2 - t0, "builder": "cuda (pc_compile_geometry)",
+                    "native": sc2.compile_timing, "identical_to_host_build": bool(same),
+                    "note": "second device compile of this process (the first one pays CUDA context creation); first frame = the full-spp frame"}
+            log(f"[bench] cold start: {cold}")
+        except Exception as e:  # never take the bench down
+            cold = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if not args.no_cpu:
@@ -452,7 +482,7 @@ def run_cuda_single(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(1, w, h, spp, args.config, sc),
         "spp_mpix_per_s": w * h * spp * args.steps / dt / 1e6, "gpu_launches": int(tot_launch), "clocks": clk,
         "e2e": {"value": e_rays / e_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-        "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ocl,
+        "roofline": roofline, "cpu_baseline": cpu, "reference_on_gpu": ocl, "cold_start": cold,
     }
     if ocl and ocl.get("value"):
         # the same-hardware baseline: the reference's own OpenCL program and launch discipline on this very GPU
@@ -720,6 +750,8 @@ def main():
     ap.add_argument("--no-opencl", action="store_true", help="skip the reference-OpenCL-kernels-on-this-GPU baseline")
     ap.add_argument("--verbose", action="store_true", help="per-step breakdown on stderr (N > 1)")
     ap.add_argument("--chains", type=int, default=0, help="override PC_OPT_SAMPLE_CHAINS (experiments)")
+    ap.add_argument("--cold-scene", action="store_true", help="N=1: also time raw triangles -> device scene compile -> first frame "
+                    "(default: only when the raw scene is in memory anyway, i.e. not loaded from POLARIS_SCENE_CACHE)")
     ap.add_argument("--exchange", default="ipc", choices=["ipc", "nccl"],
                     help="N > 1: how block rows reach rank 0 (ipc: CUDA IPC mappings + peer loads, nccl: grouped send/recv)")
     ap.add_argument("--opt", action="append", default=[], help="NAME=VALUE tracer option, e.g. PRIMARY_PACKETS=0 (experiments)")

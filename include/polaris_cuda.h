@@ -151,9 +151,13 @@ typedef enum pc_option {
                                    indirect rays sorted by (origin octant of the scene, direction octant,
                                    dominant axis) and the traversal kernels walk the rays in that order;
                                    the rays, their order in the buffers and every result stay bit-identical */
-    PC_OPT_DEFER_OCCLUSION = 9  /* 1 (default, needs PC_OPT_FUSE_TRACE): a sample's LAST occlusion test (+ emissive accumulation) runs
+    PC_OPT_DEFER_OCCLUSION = 9, /* 1 (default, needs PC_OPT_FUSE_TRACE): a sample's LAST occlusion test (+ emissive accumulation) runs
                                    inside the next sample's primary-ray launch of the same chain instead of as a launch of its
                                    own (a pure tail); the last sample's is flushed at the end of pc_trace.  Bit-identical.       */
+    PC_OPT_TRACE_REFILL = 10    /* schedule of the fused bounce-traversal kernel: 0 = every warp walks fixed 32-ray units, 1 = a warp
+                                   refills the lanes whose ray is finished from the queue and splits box steps from triangle
+                                   steps (wins on long incoherent walks: instanced / large scenes), -1 (default) = chosen at
+                                   pc_upload_scene by the size of the BVH.  Bit-identical either way.                            */
 } pc_option;
 
 /* ---- device discovery: device.GetPlatformInfo (tracer/opencl/device/platform.go) ---- */

@@ -67,12 +67,12 @@ struct DevBuf {
 // boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
     uint32_t nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0, defer = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0, defer = 0, refill = 0;
     DScene scene{};  // the captured launches carry the scene's device pointers and scalars BY VALUE: same struct, same graph
     const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
         return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
-               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && defer == o.defer && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
+               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && defer == o.defer && refill == o.refill && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
     }
 };
 
@@ -129,7 +129,9 @@ struct pc_tracer {
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS, optDeferOcc = PC_DEFAULT_DEFER_OCC;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS, optDeferOcc = PC_DEFAULT_DEFER_OCC, optRefill = -1;
+    bool refillNow = false;   // what optRefill resolves to for the uploaded scene
+    size_t innerNodes = 0;
     int occGrid = 0;
     cudaEvent_t evFork = nullptr;
     std::vector<cudaEvent_t> timerEvents;  // pairs, PC_OPT_KERNEL_TIMERS
@@ -353,7 +355,8 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
             // (pipeline.go:160-165, :203-209) are independent: one persistent launch covers both
             a = 1 - a;
             LaunchTimer lt(tr, PC_K_TRACE);
-            k_trace<COUNT><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot, sorted);
+            if (tr->refillNow) k_trace<COUNT, true><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot, sorted);
+            else k_trace<COUNT, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, fb, ctl, a, slot, sorted);
             L++;
             slot += 2;
             continue;
@@ -695,6 +698,11 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_FUSE_TRACE: tr->optFuse = value != 0; break;
         case PC_OPT_SORT_RAYS: tr->optSort = value != 0; break;
         case PC_OPT_DEFER_OCCLUSION: tr->optDeferOcc = value != 0; break;
+        case PC_OPT_TRACE_REFILL:
+            if (value < -1 || value > 1) return fail(tr, PC_ERR_INVALID_ARGUMENT, "trace refill must be -1 (by scene), 0 or 1");
+            tr->optRefill = value;
+            tr->refillNow = value < 0 ? tr->innerNodes >= PC_REFILL_AUTO_MIN_NODES : value != 0;
+            break;
         case PC_OPT_SAMPLE_CHAINS:
             if (value < 1 || value > MAX_CHAINS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample chains must be in [1, %d]", MAX_CHAINS);
             tr->optChains = value;
@@ -821,6 +829,8 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
         s.worldCellScale = make_float3(cellScale(n0[0], n0[4]), cellScale(n0[1], n0[5]), cellScale(n0[2], n0[6]));
     }
     tr->stackNeed = L.stack_need;
+    tr->innerNodes = L.node64.size() / 4;
+    tr->refillNow = tr->optRefill < 0 ? tr->innerNodes >= PC_REFILL_AUTO_MIN_NODES : tr->optRefill != 0;
     tr->hasScene = true;
     tr->sceneEpoch++;
     return 0;
@@ -917,7 +927,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; key.defer = tr->optDeferOcc; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
+            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; key.defer = tr->optDeferOcc; key.refill = tr->refillNow ? 1 : 0; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;

@@ -190,11 +190,15 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
 // registers instead of 64 (6 instead of 8 resident blocks per SM) and the kernel is latency bound, so IPC
 // falls with occupancy (2.18 -> 1.51) and k_query gets SLOWER (129 -> 148 us).  It therefore stays off by
 // default (PC_TRACE_REFILL=0: fixed 32-ray units through traverse()) until the state fits 64 registers.
-#ifndef PC_TRACE_REFILL
-#define PC_TRACE_REFILL 0
+// ROUND 2 (profiles/ab_r02d.txt): with the stack in shared memory the refilling loop fits 64 registers.  Measured per
+// kernel class: it still loses on short / coherent walks (k_primary everywhere; k_trace on the Cornell configs: 136 -> 180 us)
+// and WINS on long incoherent ones (k_trace on the instancing config 1 424 -> 1 165 us, on the terrain 1 088 -> 1 023 us).
+// It is therefore a run-time choice of the fused bounce kernel only (PC_OPT_TRACE_REFILL: 0 off, 1 on, -1 = by scene size).
+#ifndef PC_REFILL_AUTO_MIN_NODES
+#define PC_REFILL_AUTO_MIN_NODES 8192   // inner BVH nodes from which the automatic policy switches k_trace to refilling
 #endif
 #ifndef PC_REFILL_THRESHOLD
-#define PC_REFILL_THRESHOLD 26
+#define PC_REFILL_THRESHOLD 20
 #endif
 #ifndef PC_SEARCH_MIN
 #define PC_SEARCH_MIN 8
@@ -214,11 +218,10 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
     uint32_t *const name = name##_local
 #endif
 
-#if !PC_TRACE_REFILL
 // Fixed units: a warp pulls 32 consecutive rays and every lane walks its ray with traverse().
 template <bool ANY_HIT, bool COUNT, class Stack, class Source, class Sink>
-__device__ __forceinline__ void trace_queue(const DScene &sc, Stack stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
-                                            const uint32_t *perm = nullptr) {
+__device__ __forceinline__ void trace_queue_units(const DScene &sc, Stack stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+                                                  const uint32_t *perm = nullptr) {
     UnitClaim claim{0u};
     for (;;) {
         uint32_t size;
@@ -237,14 +240,13 @@ __device__ __forceinline__ void trace_queue(const DScene &sc, Stack stack, uint3
         }
     }
 }
-#else
+// Refilling schedule (see the note above)
 template <bool ANY_HIT, bool COUNT, class Stack, class Source, class Sink>
-__device__ __forceinline__ void trace_queue(const DScene &sc, Stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
-                                            const uint32_t * = nullptr) {
+__device__ __forceinline__ void trace_queue_refill(const DScene &sc, Stack stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+                                                   const uint32_t *perm = nullptr) {
     const unsigned FULL = 0xFFFFFFFFu;
     const unsigned lane = lane_id();
     const unsigned ltMask = (1u << lane) - 1u;
-    uint32_t stack[PC_STACK_SIZE];
     Trav t;
     t.cur = REF_DONE; t.sp = 0;
     uint32_t rayIndex = 0;
@@ -269,7 +271,8 @@ __device__ __forceinline__ void trace_queue(const DScene &sc, Stack, uint32_t *h
                 }
                 const uint32_t take = min(want - assigned, poolEnd - poolNext);
                 if (!busy && myRank >= assigned && myRank < assigned + take) {
-                    const uint32_t i = poolNext + (myRank - assigned);
+                    const uint32_t j = poolNext + (myRank - assigned);
+                    const uint32_t i = perm ? __ldcs(perm + j) : j;
                     float3 o, d;
                     float tmax;
                     src.load(i, o, d, tmax);
@@ -311,7 +314,12 @@ __device__ __forceinline__ void trace_queue(const DScene &sc, Stack, uint32_t *h
         }
     }
 }
-#endif
+template <bool ANY_HIT, bool COUNT, bool REFILL = false, class Stack, class Source, class Sink>
+__device__ __forceinline__ void trace_queue(const DScene &sc, Stack stack, uint32_t *head, uint32_t n, TravStats &st, Source &src, Sink &sink,
+                                            const uint32_t *perm = nullptr) {
+    if (REFILL) trace_queue_refill<ANY_HIT, COUNT>(sc, stack, head, n, st, src, sink, perm);
+    else trace_queue_units<ANY_HIT, COUNT>(sc, stack, head, n, st, src, sink, perm);
+}
 
 struct RaySource {  // rays[i] as stored by k_primary / k_shade
     const Ray *rays;
@@ -647,7 +655,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
 // accumulator), the reference only runs them back to back because its host loop is serial
 // (pipeline.go:160-165 then :203-209).  Two queue heads: every warp drains the closest-hit queue first (the
 // longer walks), then the any-hit queue, whose cheap rays make the launch's tail.  Saves one launch tail per bounce.
-template <bool COUNT>
+// REFILL: the warp-refilling schedule of trace_queue_refill instead of fixed 32-ray units.  Same results; which is faster
+// depends on the scene (PC_OPT_TRACE_REFILL).
+template <bool COUNT, bool REFILL>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot, int sorted) {
     const uint32_t nQ = (uint32_t)ctl->numRays[a], nO = (uint32_t)ctl->numRays[2];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -655,46 +665,16 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
         atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
     }
     TravStats st{0, 0, 0};
-    uint32_t missed = 0, unocc = 0;
-    const Ray *qrays = fb.rays[a], *orays = fb.rays[2];
     PC_TRAV_STACK(stack);
-    UnitClaim claim{0u};
-    for (;;) {  // the closest-hit queue first ...
-        uint32_t size;
-        const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot], nQ + nO, claim, size);
-        if (unit >= nQ) break;
-        const uint32_t j = unit + lane_id();
-        if (lane_id() < size && j < nQ) {
-            const uint32_t i = sorted ? __ldcs(fb.permInd + j) : j;
-            const Ray r = ld_ray(qrays + i);
-            Hit best;
-            const int hit = traverseWith<false, COUNT>(sc, stack, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
-            __stcs(fb.hitFlags + i, (uint32_t)hit);
-            st_hit(fb.hits + i, best.wuvt, best.inst, best.tri);
-            if (COUNT && !hit) missed++;
-        }
-    }
-    claim.seen = 0u;
-    for (;;) {  // ... then the any-hit queue, whose short walks make the launch's tail
-        uint32_t size;
-        const uint32_t unit = next_unit_adaptive(&ctl->queueHead[queueSlot + 1], nO, claim, size);
-        if (unit >= nO) break;
-        const uint32_t j = unit + lane_id();
-        if (lane_id() < size && j < nO) {
-            const uint32_t i = sorted ? __ldcs(fb.permOcc + j) : j;
-            const Ray r = ld_ray(orays + i);
-            Hit best;
-            const int hit = traverseWith<true, COUNT>(sc, stack, xyz(r.origin), xyz(r.dir), r.origin.w, best, st);
-            if (!hit) {
-                const uint32_t pixel = fb.paths[(uint32_t)r.dir.w].meta.x;  // rayGetPathIndex (util/ray.cl:26-28)
-                const float4 s = __ldcs(fb.emissiveSamples + i);
-                float4 c = fb.traceAcc[pixel];
-                c.x += s.x; c.y += s.y; c.z += s.z;
-                fb.traceAcc[pixel] = c;
-                if (COUNT) unocc++;
-            }
-        }
-    }
+    // the closest-hit queue first (the longer walks) ...
+    RaySource qsrc{fb.rays[a]};
+    HitSink<COUNT> qsink{fb.hitFlags, fb.hits, 0u};
+    trace_queue<false, COUNT, REFILL>(sc, stack, &ctl->queueHead[queueSlot], nQ, st, qsrc, qsink, sorted ? fb.permInd : nullptr);
+    // ... then the any-hit queue, whose short walks make the launch's tail
+    RaySource osrc{fb.rays[2]};
+    OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, 0u};
+    trace_queue<true, COUNT, REFILL>(sc, stack, &ctl->queueHead[queueSlot + 1], nO, st, osrc, osink, sorted ? fb.permOcc : nullptr);
+    const uint32_t missed = qsink.missed, unocc = osink.unocc;
     if (COUNT) {
         warp_add_stat(ctl, ST_NODES, st.nodes);
         warp_add_stat(ctl, ST_TRIS, st.tris);

@@ -144,7 +144,8 @@ enum Buffer { BUF_BVH_NODES = 0, BUF_MESH_INSTANCES = 1, BUF_EMISSIVES = 2, BUF_
 
 // BVH only: n volumes (bmin/bmax/center n x 3), leaf size, returns node array + leaf item lists; used directly by the
 // tests that pin bvh_builder_test.go's known answers.  leaf.ldata = -(first index into out_order), rdata = count.
-// MakeBuilder(volumes, min_leaf_items) -> object with build(std::vector<uint32_t>&) -> unique_ptr<TreeNode>, max_depth().
+// MakeBuilder(volumes, min_leaf_items) -> object with build(std::vector<uint32_t> &work) (partitions `work` in place),
+// flatten_into(nodes, work, leaf_fn) (the reference's pre-order, leaves fire the callback) and max_depth().
 template <class MakeBuilder>
 Compiled *build_bvh_only(const float *bmin, const float *bmax, const float *center, uint32_t n, int min_leaf_items,
                          uint32_t *out_order, MakeBuilder make_builder) {
@@ -154,9 +155,9 @@ Compiled *build_bvh_only(const float *bmin, const float *bmax, const float *cent
         std::vector<uint32_t> work(n);
         for (uint32_t i = 0; i < n; i++) work[i] = i;
         auto b = make_builder(v, min_leaf_items);
-        auto root = b.build(work);
+        b.build(work);
         uint32_t off = 0;
-        flatten(root.get(), c->nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t cnt) {
+        b.flatten_into(c->nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t cnt) {
             leaf.ldata = -(int32_t)off;
             leaf.rdata = (int32_t)cnt;
             for (uint32_t i = 0; i < cnt; i++) out_order[off + i] = items[i];
@@ -192,10 +193,10 @@ Compiled *compile_geometry(const RawMesh *meshes, uint32_t n_meshes, const RawIn
             for (uint32_t i = 0; i < n_insts; i++) work[i] = i;
             auto b = make_builder(v, 1);
             const double tb = now_seconds();
-            auto root = b.build(work);
+            b.build(work);
             c->timing[T_BUILD] += now_seconds() - tb;
             c->timing[T_BUILD_DEVICE] += builder_device_seconds(b, 0);
-            flatten(root.get(), c->nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t) {
+            b.flatten_into(c->nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t) {
                 leaf.ldata = -(int32_t)items[0];  // SetMeshIndex(workList[0]) only (:92-99)
                 leaf.rdata = 0;
             });
@@ -239,7 +240,7 @@ Compiled *compile_geometry(const RawMesh *meshes, uint32_t n_meshes, const RawIn
             const double t1 = now_seconds();
             c->timing[T_BOUNDS] += t1 - t0;
             auto b = make_builder(v, 10);  // minPrimitivesPerLeaf (compiler.go:19)
-            auto root = b.build(work);
+            b.build(work);
             if (b.max_depth() > c->mesh_depth) c->mesh_depth = b.max_depth();
             const double t2 = now_seconds();
             c->timing[T_BUILD] += t2 - t1;
@@ -251,13 +252,12 @@ Compiled *compile_geometry(const RawMesh *meshes, uint32_t n_meshes, const RawIn
             struct LeafRec { const uint32_t *items; uint32_t cnt, prim; };
             std::vector<LeafRec> leaves;
             std::vector<BvhNode> mesh_nodes;
-            flatten(root.get(), mesh_nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t cnt) {
+            b.flatten_into(mesh_nodes, work.data(), [&](BvhNode &leaf, const uint32_t *items, uint32_t cnt) {
                 leaf.ldata = -(int32_t)prim_offset;  // SetPrimitives(primOffset, len) (:129)
                 leaf.rdata = (int32_t)cnt;
                 leaves.push_back(LeafRec{items, cnt, prim_offset});
                 prim_offset += cnt;
             });
-            root.reset();
             const double t3 = now_seconds();
             c->timing[T_FLATTEN] += t3 - t2;
             int bad_material = 0;

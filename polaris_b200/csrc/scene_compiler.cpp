@@ -33,15 +33,18 @@ class Builder {
   public:
     Builder(const Volumes &v, int min_leaf_items) : v_(v), min_leaf_(min_leaf_items) {}
 
-    // work: item indices; scratch: same length. Returns the pointer tree.
-    std::unique_ptr<TreeNode> build(std::vector<uint32_t> &work) {
+    // work: item indices, partitioned in place into leaf order
+    void build(std::vector<uint32_t> &work) {
         scratch_.resize(work.size());
-        std::unique_ptr<TreeNode> root;
 #pragma omp parallel
 #pragma omp single
-        root = partition(work.data(), scratch_.data(), 0, (uint32_t)work.size(), 0);
+        root_ = partition(work.data(), scratch_.data(), 0, (uint32_t)work.size(), 0);
         if (!error_.empty()) throw BuildError{error_};
-        return root;
+    }
+    template <class LeafFn>
+    void flatten_into(std::vector<BvhNode> &out, const uint32_t *work, LeafFn &&leaf_fn) {
+        flatten(root_.get(), out, work, leaf_fn);
+        root_.reset();
     }
     int max_depth() const { return max_depth_; }
 
@@ -49,6 +52,7 @@ class Builder {
     const Volumes &v_;
     int min_leaf_;
     std::vector<uint32_t> scratch_;
+    std::unique_ptr<TreeNode> root_;
     std::string error_;
     int max_depth_ = 0;
 

@@ -89,8 +89,19 @@ class RawMesh:
     material: np.ndarray   # (T,) int32 index into RawScene.materials order
 
     def bbox(self):
-        v = self.vertices.reshape(-1, 3)
-        return v.min(axis=0).astype(F), v.max(axis=0).astype(F)
+        v = np.ascontiguousarray(self.vertices, dtype=F).reshape(-1, 3)
+        # min / max over axis 0 of an (N, 3) array crawls (inner dimension 3): fold long rows first
+        k = 4096
+        n = (v.shape[0] // k) * k
+        parts_lo, parts_hi = [], []
+        if n:
+            w = v[:n].reshape(-1, 3 * k)
+            parts_lo.append(w.min(axis=0).reshape(k, 3))
+            parts_hi.append(w.max(axis=0).reshape(k, 3))
+        if n < v.shape[0]:
+            parts_lo.append(v[n:])
+            parts_hi.append(v[n:])
+        return np.concatenate(parts_lo).min(axis=0).astype(F), np.concatenate(parts_hi).max(axis=0).astype(F)
 
 
 @dataclass

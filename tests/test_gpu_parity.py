@@ -161,7 +161,8 @@ def test_variants_bit_identical():
     for opts in ({}, {"primary_packets": 0}, {"use_graph": 0}, {"counters": 1}, {"reference_order": 1}, {"fuse_trace": 0},
                  {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}, {"sort_rays": 1},
                  {"sort_rays": 0}, {"sort_rays": 1, "fuse_trace": 0}, {"sort_rays": 1, "counters": 1, "use_graph": 0},
-                 {"defer_occlusion": 0}, {"defer_occlusion": 0, "use_graph": 0}, {"defer_occlusion": 1, "counters": 1}):
+                 {"defer_occlusion": 0}, {"defer_occlusion": 0, "use_graph": 0}, {"defer_occlusion": 1, "counters": 1},
+                 {"trace_refill": 1}, {"trace_refill": 0}, {"trace_refill": 1, "counters": 1, "sort_rays": 0}):
         cu = C.cuda_for(sc, w, h, **opts)
         cu.trace(T.make_block_request(w, h, spp=2), seeds)
         acc = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
@@ -193,6 +194,24 @@ def test_deferred_occlusion_bit_identical_over_many_samples():
                 assert st["kernel_launches"] > launches  # one launch per sample saved, one flush per chain added
             cu.close()
         assert res[0] == res[1], f"{chains} chains: deferring the last occlusion launch changed the result"
+
+
+@pytest.mark.parametrize("key,w,h", [("c3", 160, 96), ("c4", 160, 96)])
+def test_refilling_traversal_bit_identical(key, w, h):
+    """PC_OPT_TRACE_REFILL (the schedule the automatic policy picks for large / instanced scenes) on the two scene families
+    it is meant for: accumulator, ray totals and counters identical to fixed 32-ray units over several samples."""
+    sc = C.small_scene(key, w, h)
+    spp = 6
+    seeds = T.splitmix_seeds(13, spp * 6)
+    res = []
+    for refill in (0, 1):
+        cu = C.cuda_for(sc, w, h, trace_refill=refill, counters=1)
+        cu.trace(T.make_block_request(w, h, spp=spp), seeds)
+        st = cu.stats().device
+        res.append((cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes(), cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32).tobytes(),
+                    st["query_rays"], st["occlusion_rays"], st["unoccluded"], st["missed_query_rays"]))
+        cu.close()
+    assert res[0] == res[1]
 
 
 def test_sample_chains_equivalent():
