@@ -505,7 +505,7 @@ def run_cuda_multi(args):
 
     from polaris_b200 import tracer as T
     from polaris_b200.gather import IpcRowExchange, RowGather, StatsExchange
-    from polaris_b200.scheduler import PerfectScheduler, StaticSpeed
+    from polaris_b200.scheduler import PerfectScheduler, StaticSpeed, assign_blocks_based_on_speed
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -601,7 +601,11 @@ def run_cuda_multi(args):
     def step(e2e=False):
         i, acc0 = state["i"], state["acc"]
         feed_scheduler(i - 2)  # timings that every rank is known to hold (they were waited for during pass i-1)
-        rows = sched.schedule(speeds, h)
+        if totals["fed"] < 0 and not totals.get("primed"):  # no Stats() yet (passes 0 and 1): the naive split by Speed(), what the perfect scheduler starts with too
+            rows = list(assign_blocks_based_on_speed(speeds, h))
+            sched.block_assignment = list(rows)
+        else:
+            rows = list(sched.schedule(speeds, h))
         by = int(sum(rows[:rank]))
         req = T.make_block_request(w, h, block_y=by, block_h=int(rows[rank]), spp=pass_spp, num_bounces=NUM_BOUNCES,
                                    min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=acc0)
@@ -626,7 +630,10 @@ def run_cuda_multi(args):
             if rank != 0:
                 torch.cuda.current_stream().synchronize()  # the snapshot is taken before the next Trace clears the accumulator
         pending_merge.append((i, rows, acc0, e2e, rg))
-        pending_stats[i] = StatsExchange([rows[rank], t_trace, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"], d["device_time_ns"]], world, "cuda")
+        # Stats().RenderTime for the scheduler = the device time of the trace (CUDA events): host-side one-offs (state growing
+        # with the block, graph re-instantiation) must not look like a slow GPU
+        t_sched = d["device_time_ns"] * 1e-9 if d["device_time_ns"] else t_trace
+        pending_stats[i] = StatsExchange([rows[rank], t_sched, d["query_rays"] + d["occlusion_rays"], d["kernel_launches"], d["device_time_ns"]], world, "cuda")
         state["i"], state["acc"] = i + 1, acc0 + pass_spp
 
     # the SAME workload on ONE of these GPUs (rank 0 traces the whole frame, the others wait): the N = 1 default of this
@@ -650,6 +657,26 @@ def run_cuda_multi(args):
                        "note": "one 64-spp pass of the whole frame on rank 0's GPU alone, same scene / kernels, measured in this run"}
             log(f"[bench] the same workload on one GPU: {one_gpu['value']:.1f} Mrays/s")
         dist.barrier()
+    # The perfect scheduler converges over a few frames (scheduler.go:50-80: rows ~ BlockH / RenderTime of the previous
+    # frame, and rows near the top / bottom of this frame are cheaper than the middle).  In the interactive renderer that
+    # happens once, at start-up; here a few cheap low-spp passes with a blocking stats exchange do it before the warm-up, so
+    # that neither warm-up nor timed passes start from the naive equal split.  They also size every rank's per-block state.
+    from polaris_b200.gather import exchange_stats
+    prime_spp = max(16, pass_spp // 4)
+    for k in range(8):
+        rows = list(assign_blocks_based_on_speed(speeds, h)) if k == 0 else list(sched.schedule(speeds, h))
+        if k == 0:
+            sched.block_assignment = list(rows)
+        req = T.make_block_request(w, h, block_y=int(sum(rows[:rank])), block_h=int(rows[rank]), spp=prime_spp, num_bounces=NUM_BOUNCES,
+                                   min_bounces_for_rr=MIN_RR, exposure=EXPOSURE, accumulated_samples=pass_spp)
+        tr.trace(req, pass_seeds(0)[: prime_spp * (1 + NUM_BOUNCES)])
+        d = tr.stats().device
+        res = exchange_stats(rows[rank], d["device_time_ns"] * 1e-9, rank, world, "cuda")
+        for r in range(world):
+            speeds[r].set_stats(int(res[r][0]), float(res[r][1]))
+        if rank == 0 and args.verbose:
+            log(f"[bench] priming {k}: rows {[int(x[0]) for x in res]} device ms {[round(x[1] * 1e3, 2) for x in res]}")
+    totals["primed"] = True
     for i in range(args.warmup):
         step()
     drain()

@@ -948,6 +948,9 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
                     return fail(tr, PC_ERR_KERNEL, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
                 }
                 tr->graphKey = key;
+                // the device clock of this call starts after the (host-side, one-off) capture + instantiation: a scheduler
+                // that balances blocks by Stats() must not see it as render time
+                CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStart, s));
             }
             perSampleLaunches = tr->launchesPerSample;
             const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc);
