@@ -374,6 +374,7 @@ def run_cuda_single(args):
     seeds = T.splitmix_seeds(cfgno, spp * (1 + NUM_BOUNCES))
     tr = T.CudaTracer("cuda:0", 0)
     tr.init()
+    _lib.pin_scene(sc)  # e2e copies the scene from page-locked host memory (pc_host_register)
     tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
     tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
     tr.update_state(T.SYNCHRONOUS, T.CAMERA_DATA, sc.camera)
@@ -519,8 +520,9 @@ def run_cuda_multi(args):
     sc = objs[0]
     tr = T.CudaTracer(f"cuda:{local}", local)
     tr.init()
+    from polaris_b200 import _lib
+    _lib.pin_scene(sc)  # e2e copies the scene from page-locked host memory (pc_host_register)
     if args.chains:
-        from polaris_b200 import _lib
         tr.set_option(_lib.OPT_SAMPLE_CHAINS, args.chains)
     tr.update_state(T.SYNCHRONOUS, T.FRAME_DIMENSIONS, (w, h))
     tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)

@@ -19,7 +19,11 @@ import "C"
 import (
 	"errors"
 	"fmt"
+	"image"
+	"image/png"
 	"math/rand"
+	"os"
+	"runtime"
 	"sync"
 	"time"
 	"unsafe"
@@ -64,9 +68,33 @@ func Devices() []DeviceInfo {
 	return out
 }
 
+// PostProcessStage is the cuda backend's counterpart of opencl.PipelineStage for the post-process list
+// (tracer/opencl/pipeline.go:33-53): run by SyncFramebuffer after the tonemap, in order.
+type PostProcessStage func(tr *Tracer, blockReq *tracer.BlockRequest) (time.Duration, error)
+
+// SaveFrameBuffer writes the RGBA8 frame as a PNG, like opencl.SaveFrameBuffer (pipeline.go:216-236).
+func SaveFrameBuffer(imgFile string) PostProcessStage {
+	return func(tr *Tracer, blockReq *tracer.BlockRequest) (time.Duration, error) {
+		start := time.Now()
+		f, err := os.Create(imgFile)
+		if err != nil {
+			return 0, err
+		}
+		defer f.Close()
+		im := &image.RGBA{Pix: tr.frameBuffer, Stride: int(blockReq.FrameW) * 4,
+			Rect: image.Rect(0, 0, int(blockReq.FrameW), int(blockReq.FrameH))}
+		if err := png.Encode(f, im); err != nil {
+			return 0, err
+		}
+		return time.Since(start), nil
+	}
+}
+
 // Tracer is one CUDA device behind the tracer.Tracer interface.
 type Tracer struct {
 	sync.Mutex
+	// Stages run by SyncFramebuffer after the tonemap (renderer/cuda_backend.go fills it from Options).
+	PostProcess []PostProcessStage
 	id      string
 	ordinal int
 	handle  *C.pc_tracer
@@ -178,7 +206,7 @@ func (tr *Tracer) UpdateState(mode tracer.UpdateMode, changeType tracer.ChangeTy
 }
 
 // commitChanges: tracer/opencl/tracer.go:161-191.  The library copies every buffer during the
-// call and never retains a Go pointer (cgo pointer-passing rules).
+// call and never retains a Go pointer; see uploadScene for how the scene view satisfies cgo's pointer-passing rules.
 func (tr *Tracer) commitChanges() (time.Duration, error) {
 	if len(tr.changeBuffer) == 0 {
 		return 0, nil
@@ -227,50 +255,73 @@ func (tr *Tracer) commitChanges() (time.Duration, error) {
 	return tr.stats.UpdateTime, nil
 }
 
-func sliceView(ptr unsafe.Pointer, n int, elem uintptr) (unsafe.Pointer, C.uint64_t) {
-	if n == 0 {
-		return nil, 0
-	}
-	return ptr, C.uint64_t(uintptr(n) * elem)
-}
-
 // uploadScene: bufferSet.UploadSceneData (tracer/opencl/buffers.go:177-201); struct sizes are the
 // ones asset/scene/optimized_scene.go documents (32/80/64/80/16 bytes).
+//
+// cgo pointer passing: pc_scene_view is a struct OF pointers into Go slices.  Handing C a Go-allocated struct
+// that holds unpinned Go pointers panics under the default cgocheck ("cgo argument has Go pointer to unpinned
+// Go pointer").  Every backing array is therefore pinned with runtime.Pinner (Go >= 1.21) for the duration of
+// the call, and the view itself lives in C memory; the library copies during the call and retains nothing, so
+// everything is unpinned / freed on return.
 func (tr *Tracer) uploadScene(sc *scene.Scene) error {
-	var v C.pc_scene_view
-	if len(sc.BvhNodeList) > 0 {
-		v.bvh_nodes, v.bvh_nodes_bytes = sliceView(unsafe.Pointer(&sc.BvhNodeList[0]), len(sc.BvhNodeList), unsafe.Sizeof(sc.BvhNodeList[0]))
+	var pinner runtime.Pinner
+	defer pinner.Unpin()
+	v := (*C.pc_scene_view)(C.calloc(1, C.size_t(unsafe.Sizeof(C.pc_scene_view{}))))
+	if v == nil {
+		return ErrAllocatingBuffer
 	}
-	if len(sc.MeshInstanceList) > 0 {
-		v.mesh_instances, v.mesh_instances_bytes = sliceView(unsafe.Pointer(&sc.MeshInstanceList[0]), len(sc.MeshInstanceList), unsafe.Sizeof(sc.MeshInstanceList[0]))
+	defer C.free(unsafe.Pointer(v))
+	// pin(&slice[0]) and return (pointer, byte length); empty slices stay (nil, 0)
+	view := func(first unsafe.Pointer, pin func(), n int, elem uintptr) (unsafe.Pointer, C.uint64_t) {
+		if n == 0 {
+			return nil, 0
+		}
+		pin()
+		return first, C.uint64_t(uintptr(n) * elem)
 	}
-	if len(sc.MaterialNodeList) > 0 {
-		v.material_nodes, v.material_nodes_bytes = sliceView(unsafe.Pointer(&sc.MaterialNodeList[0]), len(sc.MaterialNodeList), unsafe.Sizeof(sc.MaterialNodeList[0]))
+	if n := len(sc.BvhNodeList); n > 0 {
+		p := &sc.BvhNodeList[0]
+		v.bvh_nodes, v.bvh_nodes_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.TextureData) > 0 {
-		v.texture_data, v.texture_data_bytes = sliceView(unsafe.Pointer(&sc.TextureData[0]), len(sc.TextureData), 1)
+	if n := len(sc.MeshInstanceList); n > 0 {
+		p := &sc.MeshInstanceList[0]
+		v.mesh_instances, v.mesh_instances_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.TextureMetadata) > 0 {
-		v.texture_metadata, v.texture_metadata_bytes = sliceView(unsafe.Pointer(&sc.TextureMetadata[0]), len(sc.TextureMetadata), unsafe.Sizeof(sc.TextureMetadata[0]))
+	if n := len(sc.MaterialNodeList); n > 0 {
+		p := &sc.MaterialNodeList[0]
+		v.material_nodes, v.material_nodes_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.VertexList) > 0 {
-		v.vertices, v.vertices_bytes = sliceView(unsafe.Pointer(&sc.VertexList[0]), len(sc.VertexList), unsafe.Sizeof(sc.VertexList[0]))
+	if n := len(sc.TextureData); n > 0 {
+		p := &sc.TextureData[0]
+		v.texture_data, v.texture_data_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, 1)
 	}
-	if len(sc.NormalList) > 0 {
-		v.normals, v.normals_bytes = sliceView(unsafe.Pointer(&sc.NormalList[0]), len(sc.NormalList), unsafe.Sizeof(sc.NormalList[0]))
+	if n := len(sc.TextureMetadata); n > 0 {
+		p := &sc.TextureMetadata[0]
+		v.texture_metadata, v.texture_metadata_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.UvList) > 0 {
-		v.uvs, v.uvs_bytes = sliceView(unsafe.Pointer(&sc.UvList[0]), len(sc.UvList), unsafe.Sizeof(sc.UvList[0]))
+	if n := len(sc.VertexList); n > 0 {
+		p := &sc.VertexList[0]
+		v.vertices, v.vertices_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.MaterialIndex) > 0 {
-		v.material_indices, v.material_indices_bytes = sliceView(unsafe.Pointer(&sc.MaterialIndex[0]), len(sc.MaterialIndex), 4)
+	if n := len(sc.NormalList); n > 0 {
+		p := &sc.NormalList[0]
+		v.normals, v.normals_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
-	if len(sc.EmissivePrimitives) > 0 {
-		v.emissives, v.emissives_bytes = sliceView(unsafe.Pointer(&sc.EmissivePrimitives[0]), len(sc.EmissivePrimitives), unsafe.Sizeof(sc.EmissivePrimitives[0]))
+	if n := len(sc.UvList); n > 0 {
+		p := &sc.UvList[0]
+		v.uvs, v.uvs_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
+	}
+	if n := len(sc.MaterialIndex); n > 0 {
+		p := &sc.MaterialIndex[0]
+		v.material_indices, v.material_indices_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, 4)
+	}
+	if n := len(sc.EmissivePrimitives); n > 0 {
+		p := &sc.EmissivePrimitives[0]
+		v.emissives, v.emissives_bytes = view(unsafe.Pointer(p), func() { pinner.Pin(p) }, n, unsafe.Sizeof(*p))
 	}
 	v.scene_diffuse_mat_index = C.int32_t(sc.SceneDiffuseMatIndex)
 	v.scene_emissive_mat_index = C.int32_t(sc.SceneEmissiveMatIndex)
-	if rc := C.pc_upload_scene(tr.handle, &v); rc != 0 {
+	if rc := C.pc_upload_scene(tr.handle, v); rc != 0 {
 		return tr.lastError(rc)
 	}
 	tr.hasScene = true
@@ -450,6 +501,11 @@ func (tr *Tracer) SyncFramebuffer(blockReq *tracer.BlockRequest) (time.Duration,
 	}
 	if rc := C.pc_sync_framebuffer(tr.handle, &req, out); rc != 0 {
 		return time.Since(start), tr.lastError(rc)
+	}
+	for _, stage := range tr.PostProcess { // tracer.go:262-270
+		if _, err := stage(tr, blockReq); err != nil {
+			return time.Since(start), err
+		}
 	}
 	return time.Since(start), nil
 }

@@ -299,6 +299,12 @@ void pc_compiled_depths(void *compiled, int *top_depth, int *mesh_depth);
 void pc_compiled_timing(void *compiled, double *out8);
 void pc_compiled_free(void *compiled);
 
+/* ---- pinned host memory: page-lock (and later release) a caller-owned buffer -- scene arrays before pc_upload_scene, the
+ * RGBA8 frame handed to pc_sync_framebuffer -- so the copies run at full host-link rate.  Optional; the library never
+ * retains host pointers either way.  Registering a range twice is not an error. */
+int pc_host_register(void *ptr, uint64_t bytes);
+int pc_host_unregister(void *ptr);
+
 /* ---- test / oracle hooks ---- */
 int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes);
 /* Upload n rays (32 B each) into rays0 and run one intersection kernel on them:

@@ -126,6 +126,8 @@ SYMBOLS = [
     ("pc_ipc_close", ctypes.c_int, [vp, vp]),
     ("pc_wait_for_kernels", ctypes.c_int, [vp]),
     ("pc_sync_framebuffer", ctypes.c_int, [vp, _P(BlockRequest), vp]),
+    ("pc_host_register", ctypes.c_int, [vp, u64]),
+    ("pc_host_unregister", ctypes.c_int, [vp]),
     ("pc_read_buffer", ctypes.c_int, [vp, ctypes.c_int, vp, u64]),
     ("pc_debug_frame_count", u32, [u32, u32]),
     ("pc_trace_debug", ctypes.c_int, [vp, _P(BlockRequest), vp, ctypes.c_size_t, u32, vp, u64, vp, u32, _P(u32), _P(Stats)]),
@@ -159,6 +161,26 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+def pin_scene(scene) -> list:
+    """Page-lock the scene's ten flat arrays in place (pc_host_register); returns the arrays to hand to unpin()."""
+    lib = load()
+    pinned = []
+    for field in scene._SECTIONS:
+        a = getattr(scene, field)
+        if not a.flags["C_CONTIGUOUS"]:
+            a = np.ascontiguousarray(a)
+            setattr(scene, field, a)
+        if a.nbytes and lib.pc_host_register(a.ctypes.data, a.nbytes) == 0:
+            pinned.append(a)
+    return pinned
+
+
+def unpin(arrays):
+    lib = load()
+    for a in arrays:
+        lib.pc_host_unregister(a.ctypes.data)
 
 
 def scene_view(scene) -> tuple[SceneView, list]:

@@ -1247,6 +1247,22 @@ int pc_sync_framebuffer(pc_tracer *tr, const pc_block_request *req, uint8_t *rgb
     return 0;
 }
 
+// Page-lock caller-owned host memory so that the copies of pc_upload_scene / pc_sync_framebuffer run at full PCIe / C2C
+// rate and asynchronously (the reference gets the same effect from CL_MEM_USE_HOST_PTR, device/buffer.go:98-104).
+int pc_host_register(void *ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return PC_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return PC_ERR_ALLOC; }
+    return 0;
+}
+int pc_host_unregister(void *ptr) {
+    if (!ptr) return PC_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return PC_ERR_INVALID_ARGUMENT; }
+    return 0;
+}
+
 int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes) {
     int rc = enter(tr);
     if (rc) return rc;

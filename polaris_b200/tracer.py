@@ -225,10 +225,13 @@ class _HandleTracer(Tracer):
         t0 = time.perf_counter()
         if not self._has_scene:
             raise ErrNoSceneData(_lib.ERR_NO_SCENE_DATA, "no scene data uploaded")
-        out = np.empty((block_req.frame_h, block_req.frame_w, 4), dtype=np.uint8) if want_pixels else None
+        out = self._frame_out(block_req.frame_h, block_req.frame_w) if want_pixels else None
         self._check(self._fn("sync_framebuffer")(self._h, ctypes.byref(block_req), out.ctypes.data if want_pixels else None))
         self.frame_buffer = out
         return time.perf_counter() - t0
+
+    def _frame_out(self, h, w):
+        return np.empty((h, w, 4), dtype=np.uint8)
 
     # -- test hooks
     def set_option(self, option, value):
@@ -266,6 +269,9 @@ class CudaTracer(_HandleTracer):
 
     def close(self):
         if self._h is not None:
+            if getattr(self, "_pinned_frame", None) is not None:
+                self._lib.pc_host_unregister(self._pinned_frame.ctypes.data)
+                self._pinned_frame = None
             self._lib.pc_destroy(self._h)
             self._h = None
         self._has_scene = False
@@ -273,6 +279,17 @@ class CudaTracer(_HandleTracer):
 
     def flags(self):
         return int(self._lib.pc_flags(self._h))
+
+    def _frame_out(self, h, w):
+        # one page-locked RGBA8 frame per tracer, reused by every SyncFramebuffer (the caller copies it if it keeps it)
+        buf = getattr(self, "_pinned_frame", None)
+        if buf is None or buf.shape[:2] != (h, w):
+            if buf is not None:
+                self._lib.pc_host_unregister(buf.ctypes.data)
+            buf = np.empty((h, w, 4), dtype=np.uint8)
+            self._lib.pc_host_register(buf.ctypes.data, buf.nbytes)
+            self._pinned_frame = buf
+        return buf
 
     def speed(self):
         return int(self._lib.pc_speed(self._h))

@@ -106,3 +106,19 @@ def test_c99_client_compiles_and_links(tmp_path):
         exe = _build_c_client(tmp_path, name)
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 2 and "usage" in r.stderr  # no GPU work without arguments
+
+
+def test_go_backend_patch_applies_to_the_reference():
+    """go/polaris-cuda-backend.patch is a real unified diff against the reference checkout (renderer/default.go:199-253,
+    renderer/options.go, cmd/render.go:61-65, cmd/list_devices.go, main.go): `patch --dry-run` must accept it.  Skipped
+    where the reference is absent (the GPU box)."""
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir("/root/reference/renderer") or not shutil.which("patch"):
+        pytest.skip("reference checkout or patch(1) not available")
+    with open(os.path.join(root, "go", "polaris-cuda-backend.patch")) as f:
+        r = subprocess.run(["patch", "--dry-run", "-p1", "-d", "/root/reference"], stdin=f, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "renderer/cuda_backend.go" in r.stdout and "renderer/default.go" in r.stdout
