@@ -308,9 +308,13 @@ def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, config):
     st["_spp"], st["_background"] = prof_spp, sc.scene_diffuse_mat_index != -1
     by = algorithmic_bytes(st, w * block_h, NUM_BOUNCES)
     names = _lib.KERNEL_CLASS_NAMES
-    assert len(cls) % prof_spp == 0, (len(cls), prof_spp)
-    lps = len(cls) // prof_spp  # launches per sample, the same class sequence every sample
-    cls2, us2 = cls.reshape(prof_spp, lps), us.reshape(prof_spp, lps).astype(np.float64)
+    # the launch sequence repeats per BATCH (a set of launches carries several samples, PC_OPT_SAMPLE_SLOTS): the period is
+    # the distance between two k_begin_sample launches
+    begins = np.nonzero(cls == _lib.K_BEGIN_SAMPLE)[0]
+    lps = int(begins[1] - begins[0]) if len(begins) > 1 else len(cls)
+    assert len(cls) % lps == 0, (len(cls), lps)
+    n_batches = len(cls) // lps
+    cls2, us2 = cls.reshape(n_batches, lps), us.reshape(n_batches, lps).astype(np.float64)
     assert (cls2 == cls2[0]).all()
     med_us, mean_us, counts = {}, {}, {}
     for ci, n in enumerate(names):
@@ -329,10 +333,10 @@ def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, config):
     total = sum(med_us.values())
     dom = max(classes, key=lambda k: med_us[k])
     peak, peak_src = measured_hbm_peak()
-    kern = {k: {"launches_per_sample": counts[k], "avg_us": med_us[k] / counts[k], "mean_avg_us": mean_us[k] / counts[k],
-                "share": med_us[k] / total, "alg_GBps": by[k] / prof_spp / (med_us[k] * 1e3)} for k in classes}
-    log("[bench] kernel classes (median over %d samples): %s" % (prof_spp, json.dumps(kern)))
-    achieved = by[dom] / prof_spp / (med_us[dom] * 1e3)  # bytes per ns == GB/s
+    kern = {k: {"launches_per_batch": counts[k], "avg_us": med_us[k] / counts[k], "mean_avg_us": mean_us[k] / counts[k],
+                "share": med_us[k] / total, "alg_GBps": by[k] / n_batches / (med_us[k] * 1e3)} for k in classes}
+    log("[bench] kernel classes (median over %d batches of %d samples): %s" % (n_batches, prof_spp // n_batches, json.dumps(kern)))
+    achieved = by[dom] / n_batches / (med_us[dom] * 1e3)  # bytes per ns == GB/s
     avg_launch_us = med_us[dom] / counts[dom]
     rays = st["query_rays"] + st["occlusion_rays"]
     prof = measured_profile(config, dom)
@@ -348,8 +352,9 @@ def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, config):
         measured["note"] = ("ncu --set full of this kernel class on this config (profiles/); bytes are per launch, rates use the "
                             "launch time measured HERE.  bound = what the counters show limits the kernel")
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / prof_spp / counts[dom],
-            "avg_launch_us": avg_launch_us, "timing": f"median over {prof_spp} samples after a warm-up trace, CUDA events per launch",
+            "traffic": traffic, "peak_source": peak_src, "bytes_per_launch": by[dom] / n_batches / counts[dom],
+            "avg_launch_us": avg_launch_us, "samples_per_launch": prof_spp // n_batches,
+            "timing": f"median over {n_batches} batches ({prof_spp} samples) after a warm-up trace, CUDA events per launch",
             "kernels": kern, "measured": measured,
             "rays_per_path": rays / (w * block_h * prof_spp), "nodes_per_ray": st["nodes_tested"] / max(1, rays),
             "tris_per_ray": st["tris_tested"] / max(1, rays)}

@@ -154,6 +154,10 @@ typedef enum pc_option {
     PC_OPT_DEFER_OCCLUSION = 9, /* 1 (default, needs PC_OPT_FUSE_TRACE): a sample's LAST occlusion test (+ emissive accumulation) runs
                                    inside the next sample's primary-ray launch of the same chain instead of as a launch of its
                                    own (a pure tail); the last sample's is flushed at the end of pc_trace.  Bit-identical.       */
+    PC_OPT_SAMPLE_SLOTS = 11,   /* samples one set of launches carries per chain: 1..8, 0 (default) = enough for ~4 M paths per launch
+                                   (one sample of a 1 Mpx block does not fill the machine).  The ray buffers stay flat, slot after
+                                   slot; every sample keeps its own accumulator, seeds and ray numbering, so results are
+                                   bit-identical to tracing the samples one by one (tested).                                */
     PC_OPT_TRACE_REFILL = 10    /* schedule of the fused bounce-traversal kernel: 0 = every warp walks fixed 32-ray units, 1 = a warp
                                    refills the lanes whose ray is finished from the queue and splits box steps from triangle
                                    steps (wins on long incoherent walks: instanced / large scenes), -1 (default) = chosen at

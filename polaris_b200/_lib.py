@@ -65,7 +65,7 @@ assert ctypes.sizeof(BlockRequest) == 48
 BUF_RAYS0, BUF_RAYS1, BUF_RAYS2, BUF_PATHS, BUF_HIT_FLAGS, BUF_INTERSECTIONS = 0, 1, 2, 3, 4, 5
 BUF_EMISSIVE_SAMPLES, BUF_TRACE_ACCUMULATOR, BUF_FRAME_ACCUMULATOR, BUF_FRAME_BUFFER, BUF_RAY_COUNTERS = 6, 7, 8, 9, 10
 # pc_option
-OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE, OPT_SORT_RAYS, OPT_DEFER_OCCLUSION, OPT_TRACE_REFILL = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+OPT_COUNTERS, OPT_PRIMARY_PACKETS, OPT_REFERENCE_ORDER, OPT_USE_GRAPH, OPT_FIX_Q4, OPT_KERNEL_TIMERS, OPT_SAMPLE_CHAINS, OPT_FUSE_TRACE, OPT_SORT_RAYS, OPT_DEFER_OCCLUSION, OPT_TRACE_REFILL, OPT_SAMPLE_SLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
 K_BEGIN_SAMPLE, K_PRIMARY, K_SHADE, K_OCCLUSION, K_QUERY, K_TRACE = 0, 1, 2, 3, 4, 5
 KERNEL_CLASS_NAMES = ["k_begin_sample", "k_primary", "k_shade", "k_occlusion", "k_query", "k_trace"]
 # pc_debug_flag == opencl.DebugFlag (tracer/opencl/pipeline.go:17-30)

@@ -67,12 +67,12 @@ struct DevBuf {
 // boundaries every frame, or an interactive camera, never forces a re-instantiation.
 struct GraphKey {
     uint32_t nb = 0, rr = 0;
-    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, fuse = 0, sort = 0, defer = 0, refill = 0;
+    int counters = 0, packets = 0, reforder = 0, fixq4 = 0, chains = 0, slots = 0, fuse = 0, sort = 0, defer = 0, refill = 0;
     DScene scene{};  // the captured launches carry the scene's device pointers and scalars BY VALUE: same struct, same graph
     const void *seedsPtr = nullptr;
     bool operator==(const GraphKey &o) const {
         return nb == o.nb && rr == o.rr && counters == o.counters && packets == o.packets && reforder == o.reforder &&
-               fixq4 == o.fixq4 && chains == o.chains && fuse == o.fuse && sort == o.sort && defer == o.defer && refill == o.refill && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
+               fixq4 == o.fixq4 && chains == o.chains && slots == o.slots && fuse == o.fuse && sort == o.sort && defer == o.defer && refill == o.refill && memcmp(&scene, &o.scene, sizeof(DScene)) == 0 && seedsPtr == o.seedsPtr;
     }
 };
 
@@ -84,16 +84,17 @@ struct ReadFence {
 };
 
 constexpr int MAX_CHAINS = 8;
-constexpr int GRAPH_SAMPLES_PER_CHAIN = 4;  // samples each chain contributes to one replay of the captured graph
+constexpr int GRAPH_SAMPLES_PER_CHAIN = 4;  // samples each chain and slot contributes to one replay of the captured graph (batches per chain)
 struct Chain {
-    DevBuf rays[3], paths, hitFlags, hits, emSamples, ctl, status, acc, permOcc, permInd;  // acc: chains > 0 only
+    DevBuf rays[3], paths, hitFlags, hits, emSamples, ctl, status, permOcc, permInd;
+    DevBuf accs[MAX_SLOTS];  // one accumulator per sample slot (chain 0 / slot 0 is the handle's trace accumulator)
     FrameBufs fb{};
     cudaStream_t stream = nullptr;  // chain 0 uses the handle's stream
     cudaEvent_t evJoin = nullptr;
     // rows [dirtyY0, dirtyY1) of this chain's accumulator (chain 0: the trace accumulator) may be non-zero: the next
     // pc_trace clears those and its own block instead of the whole frame (the reference clears W*H every Trace,
     // tracer.go:215; the observable state -- zero outside the traced block -- is the same)
-    uint32_t dirtyY0 = 0, dirtyY1 = 0;
+    uint32_t dirtyY0[MAX_SLOTS] = {}, dirtyY1[MAX_SLOTS] = {};
 };
 
 }  // namespace
@@ -121,15 +122,18 @@ struct pc_tracer {
     // stream, and the chains' launches overlap.  Chain 0 accumulates into the trace accumulator, every
     // other chain into its own, added to it once at the end of pc_trace in chain order (deterministic).
     Chain chain[MAX_CHAINS];
-    size_t rayCap = 0;      // rays the per-chain ray / path / hit state holds: sized by the largest BLOCK traced so far
-                            // (+ slack), not by the frame -- at 8 GPUs a rank holds 1/8 of it
+    size_t rayCap = 0;      // rays PER SAMPLE SLOT the per-chain ray / path / hit state holds: sized by the largest BLOCK
+                            // traced so far (+ slack), not by the frame
+    int raySlots = 0;       // sample slots the per-chain state holds (rayCap * raySlots rays per buffer)
+    int lastSlot = 0;       // slot of the last sample of the last pc_trace (pc_read_buffer)
+    uint32_t lastSlotPaths = 0, lastBounces = 1;
     int nChains = 0;        // chains with allocated state
     int lastChain = 0;      // chain that traced the last sample of the last pc_trace (pc_read_buffer)
     size_t statusStride = 0;  // words per bounce
     CameraParams cam{};
     bool hasCamera = false;
     // options
-    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS, optDeferOcc = PC_DEFAULT_DEFER_OCC, optRefill = -1;
+    int optCounters = 0, optPackets = 0, optRefOrder = 0, optGraph = 1, optFixQ4 = 1, optTimers = 0, optChains = 4, optFuse = PC_DEFAULT_FUSE_TRACE, optSort = PC_DEFAULT_SORT_RAYS, optDeferOcc = PC_DEFAULT_DEFER_OCC, optRefill = -1, optSlots = 0;
     bool refillNow = false;   // what optRefill resolves to for the uploaded scene
     size_t innerNodes = 0;
     int occGrid = 0;
@@ -304,7 +308,8 @@ static bool defer_last_occlusion(const pc_tracer *tr, bool dbg) {
 static int last_occlusion_slot(uint32_t nb) { return 1 + 2 * ((int)nb - 1); }  // == the slot the un-deferred launch uses
 
 template <bool COUNT>
-void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches, DebugSink *dbg) {
+void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleAdvance, uint32_t nSlots, uint32_t slotStride,
+                     uint64_t *launches, DebugSink *dbg) {
     cudaStream_t s = ch.stream;
     TraceCtl *ctl = (TraceCtl *)ch.ctl.p;
     const uint32_t *seeds = (const uint32_t *)tr->seedsDev.p;
@@ -320,7 +325,7 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     size_t statusWords = tr->statusStride * nb;
     {
         LaunchTimer lt(tr, PC_K_BEGIN_SAMPLE);
-        k_begin_sample<<<grid_for(statusWords, 256, 1024), 256, 0, s>>>(ctl, status, statusWords, sampleStride);
+        k_begin_sample<<<grid_for(statusWords, 256, 1024), 256, 0, s>>>(ctl, status, statusWords, sampleAdvance, nSlots, slotStride);
     }
     L++;
     int slot = 0;
@@ -366,9 +371,9 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
         {
         LaunchTimer lt(tr, PC_K_OCCLUSION);
         if (tr->optRefOrder)
-            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
+            k_occlusion<true, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb, 1, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
         else
-            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
+            k_occlusion<false, COUNT><<<tr->occGrid, TRAV_BLOCK, 0, s>>>(tr->sc, fb.rays[2], fb.paths, fb.emissiveSamples, fb, 1, dbg ? fb.hitFlags : nullptr, ctl, slot, sorted && !dbg ? fb.permOcc : nullptr);
         }
         L++;
         slot++;
@@ -390,15 +395,19 @@ void record_sample_t(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint
     *launches = L;
 }
 
-void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleStride, uint64_t *launches, DebugSink *dbg = nullptr) {
-    if (tr->optCounters) record_sample_t<true>(tr, ch, req, sampleStride, launches, dbg);
-    else record_sample_t<false>(tr, ch, req, sampleStride, launches, dbg);
+// One BATCH of a chain: nSlots samples (curSample, curSample + slotStride, ...) through one set of launches.
+void record_sample(pc_tracer *tr, Chain &ch, const pc_block_request &req, uint32_t sampleAdvance, uint32_t nSlots, uint32_t slotStride,
+                   uint64_t *launches, DebugSink *dbg = nullptr) {
+    if (tr->optCounters) record_sample_t<true>(tr, ch, req, sampleAdvance, nSlots, slotStride, launches, dbg);
+    else record_sample_t<false>(tr, ch, req, sampleAdvance, nSlots, slotStride, launches, dbg);
 }
 
 // Enqueue perChain[c] samples on every chain c < nChains: fork the chain streams off the handle's stream,
 // let each chain run its samples back to back, join.  Works identically under stream capture (the fork /
 // join events become graph dependencies and the chains become parallel branches of the graph).
-int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, const uint32_t *perChain, uint64_t *launchesPerSample,
+// perChain[c] = samples of chain c, traced as batches of up to `slots` samples per set of launches.  *launchTotal
+// accumulates the number of launches.
+int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, int slots, const uint32_t *perChain, uint64_t *launchTotal,
                    bool flushOcclusion = false, uint64_t *flushLaunches = nullptr) {
     cudaStream_t s0 = tr->stream;
     if (nChains > 1) {
@@ -407,16 +416,21 @@ int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, cons
             if ((perChain[c] || flushOcclusion) && cudaStreamWaitEvent(tr->chain[c].stream, tr->evFork, 0) != cudaSuccess) return 1;
     }
     for (int c = 0; c < nChains; c++) {
-        for (uint32_t k = 0; k < perChain[c]; k++) record_sample(tr, tr->chain[c], req, (uint32_t)nChains, launchesPerSample);
+        for (uint32_t k = 0; k < perChain[c]; k += (uint32_t)slots) {
+            const uint32_t nSlots = perChain[c] - k < (uint32_t)slots ? perChain[c] - k : (uint32_t)slots;
+            uint64_t L = 0;
+            record_sample(tr, tr->chain[c], req, (uint32_t)(nChains * slots), nSlots, (uint32_t)nChains, &L);
+            if (launchTotal) *launchTotal += L;
+        }
         if (flushOcclusion) {  // the chain's last sample left its last bounce's occlusion rays behind (see k_primary)
             Chain &ch = tr->chain[c];
             const int sorted = tr->optSort && !tr->optRefOrder ? 1 : 0;
             // its own queue head: the sample's k_primary already pulled from last_occlusion_slot (for the sample before it)
             const int flushSlot = last_occlusion_slot(req.num_bounces) + 1;
             if (tr->optCounters)
-                k_occlusion<false, true><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb.traceAcc, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
+                k_occlusion<false, true><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb, 1, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
             else
-                k_occlusion<false, false><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb.traceAcc, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
+                k_occlusion<false, false><<<tr->occGrid, TRAV_BLOCK, 0, ch.stream>>>(tr->sc, ch.fb.rays[2], ch.fb.paths, ch.fb.emissiveSamples, ch.fb, 1, nullptr, (TraceCtl *)ch.ctl.p, flushSlot, sorted ? ch.fb.permOcc : nullptr);
             if (flushLaunches) (*flushLaunches)++;
         }
     }
@@ -428,15 +442,16 @@ int enqueue_chains(pc_tracer *tr, const pc_block_request &req, int nChains, cons
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
 
-// (Re)allocate the per-chain state: `want` chains, each able to hold `needRays` rays (the block being traced).
-// Growing re-allocates every chain (new device addresses: the captured graph is dropped); the capacity only grows, with
-// 1/8 slack, so the perfect scheduler nudging row boundaries from pass to pass does not re-allocate.
-int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
+// (Re)allocate the per-chain state: `want` chains, each able to hold `slots` samples of `needRays` rays (the block being
+// traced).  Growing re-allocates every chain (new device addresses: the captured graph is dropped); the capacity only
+// grows, with 1/8 slack, so the perfect scheduler nudging row boundaries from pass to pass does not re-allocate.
+int ensure_chains(pc_tracer *tr, int want, size_t needRays, int slots = 1) {
     if (want < 1) want = 1;
     if (want > MAX_CHAINS) want = MAX_CHAINS;
+    if (slots < 1) slots = 1;
     const size_t px = (size_t)tr->W * tr->H;
     if (needRays > px) needRays = px;
-    if (needRays > tr->rayCap) {
+    if (needRays > tr->rayCap || slots > tr->raySlots) {
         CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
         drop_graph(tr);
         for (int c = 0; c < MAX_CHAINS; c++) {
@@ -444,14 +459,32 @@ int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
             DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.permOcc, &ch.permInd};
             for (DevBuf *b : all) b->release();
         }
-        size_t cap = needRays + needRays / 8;
-        cap = (cap + 1023) / 1024 * 1024;
-        tr->rayCap = cap > px ? px : cap;
-        tr->statusStride = tr->rayCap / SHADE_TILE + 2;  // one look-back word per k_shade tile (+ the partial one)
+        if (needRays > tr->rayCap) {
+            size_t cap = needRays + needRays / 8;
+            cap = (cap + 1023) / 1024 * 1024;
+            tr->rayCap = cap > px ? px : cap;
+        }
+        if (slots > tr->raySlots) tr->raySlots = slots;
+        tr->statusStride = tr->rayCap * tr->raySlots / SHADE_TILE + 2;  // one look-back word per k_shade tile (+ the partial one)
         want = want > tr->nChains ? want : tr->nChains;
         tr->nChains = 0;
     }
-    const size_t cap = tr->rayCap;
+    const size_t cap = tr->rayCap * (size_t)tr->raySlots;
+    for (int c = 0; c < want; c++) {
+        Chain &ch = tr->chain[c];
+        // the slots' accumulators: frame indexed like the trace accumulator; only block rows are ever touched
+        for (int sl = 0; sl < tr->raySlots; sl++) {
+            if (c == 0 && sl == 0) continue;
+            if (ch.accs[sl].bytes != px * 16) {
+                CU(tr, PC_ERR_ALLOC, ch.accs[sl].alloc(px * 16));
+                CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.accs[sl].p, 0, ch.accs[sl].bytes, tr->stream));
+                ch.dirtyY0[sl] = ch.dirtyY1[sl] = 0;
+            }
+        }
+        for (int sl = 0; sl < MAX_SLOTS; sl++)
+            ch.fb.slotAcc[sl] = (float4 *)(c == 0 && sl == 0 ? tr->traceAcc.p : (sl < tr->raySlots ? ch.accs[sl].p : nullptr));
+        ch.fb.traceAcc = ch.fb.slotAcc[0];
+    }
     for (int c = tr->nChains; c < want; c++) {
         Chain &ch = tr->chain[c];
         if (c == 0) ch.stream = tr->stream;
@@ -471,11 +504,6 @@ int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
             CU(tr, PC_ERR_ALLOC, ch.ctl.alloc(sizeof(TraceCtl)));
             CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.ctl.p, 0, sizeof(TraceCtl), tr->stream));
         }
-        if (c > 0 && ch.acc.bytes != px * 16) {  // frame indexed like the trace accumulator; only block rows are ever touched
-            CU(tr, PC_ERR_ALLOC, ch.acc.alloc(px * 16));
-            CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ch.acc.p, 0, ch.acc.bytes, tr->stream));
-            ch.dirtyY0 = ch.dirtyY1 = 0;
-        }
         for (int i = 0; i < 3; i++) ch.fb.rays[i] = (Ray *)ch.rays[i].p;
         ch.fb.paths = (PathRec *)ch.paths.p;
         ch.fb.hitFlags = (uint32_t *)ch.hitFlags.p;
@@ -483,7 +511,6 @@ int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
         ch.fb.emissiveSamples = (float4 *)ch.emSamples.p;
         ch.fb.permOcc = (uint32_t *)ch.permOcc.p;
         ch.fb.permInd = (uint32_t *)ch.permInd.p;
-        ch.fb.traceAcc = (float4 *)(c == 0 ? tr->traceAcc.p : ch.acc.p);
         DevBuf *zero[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status};
         for (DevBuf *b : zero) CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(b->p, 0, b->bytes, tr->stream));
         tr->nChains = c + 1;
@@ -494,12 +521,13 @@ int ensure_chains(pc_tracer *tr, int want, size_t needRays) {
 void release_chain_buffers(pc_tracer *tr) {
     for (int c = 0; c < MAX_CHAINS; c++) {
         Chain &ch = tr->chain[c];
-        DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.acc, &ch.permOcc, &ch.permInd};
+        DevBuf *all[] = {&ch.rays[0], &ch.rays[1], &ch.rays[2], &ch.paths, &ch.hitFlags, &ch.hits, &ch.emSamples, &ch.status, &ch.permOcc, &ch.permInd};
         for (DevBuf *b : all) b->release();
-        ch.dirtyY0 = ch.dirtyY1 = 0;
+        for (int sl = 0; sl < MAX_SLOTS; sl++) { ch.accs[sl].release(); ch.dirtyY0[sl] = ch.dirtyY1[sl] = 0; }
     }
     tr->nChains = 0;
     tr->rayCap = 0;
+    tr->raySlots = 0;
 }
 
 int upload(pc_tracer *tr, DevBuf &b, const void *src, size_t bytes) {
@@ -519,18 +547,18 @@ int clear_rows(pc_tracer *tr, void *acc, uint32_t y0, uint32_t y1, cudaStream_t 
 
 // ClearTraceAccumulator (tracer.go:215) without touching rows that are zero already: clear what earlier traces left
 // behind and the block about to be traced, remember the new block as the dirty range.
-int clear_for_block(pc_tracer *tr, Chain &ch, void *acc, uint32_t y0, uint32_t y1, cudaStream_t s) {
+int clear_for_block(pc_tracer *tr, uint32_t &dirtyY0, uint32_t &dirtyY1, void *acc, uint32_t y0, uint32_t y1, cudaStream_t s) {
     int rc = 0;
-    if (ch.dirtyY1 > ch.dirtyY0 && (ch.dirtyY1 < y0 || ch.dirtyY0 > y1)) {  // disjoint: two clears
-        if ((rc = clear_rows(tr, acc, ch.dirtyY0, ch.dirtyY1, s))) return rc;
+    if (dirtyY1 > dirtyY0 && (dirtyY1 < y0 || dirtyY0 > y1)) {  // disjoint: two clears
+        if ((rc = clear_rows(tr, acc, dirtyY0, dirtyY1, s))) return rc;
         rc = clear_rows(tr, acc, y0, y1, s);
     } else {
-        const uint32_t lo = ch.dirtyY1 > ch.dirtyY0 && ch.dirtyY0 < y0 ? ch.dirtyY0 : y0;
-        const uint32_t hi = ch.dirtyY1 > ch.dirtyY0 && ch.dirtyY1 > y1 ? ch.dirtyY1 : y1;
+        const uint32_t lo = dirtyY1 > dirtyY0 && dirtyY0 < y0 ? dirtyY0 : y0;
+        const uint32_t hi = dirtyY1 > dirtyY0 && dirtyY1 > y1 ? dirtyY1 : y1;
         rc = clear_rows(tr, acc, lo, hi, s);
     }
-    ch.dirtyY0 = y0;
-    ch.dirtyY1 = y1;
+    dirtyY0 = y0;
+    dirtyY1 = y1;
     return rc;
 }
 
@@ -698,6 +726,10 @@ int pc_set_option(pc_tracer *tr, int option, int value) {
         case PC_OPT_FUSE_TRACE: tr->optFuse = value != 0; break;
         case PC_OPT_SORT_RAYS: tr->optSort = value != 0; break;
         case PC_OPT_DEFER_OCCLUSION: tr->optDeferOcc = value != 0; break;
+        case PC_OPT_SAMPLE_SLOTS:
+            if (value < 0 || value > MAX_SLOTS) return fail(tr, PC_ERR_INVALID_ARGUMENT, "sample slots must be in [0, %d] (0 = by block size)", MAX_SLOTS);
+            tr->optSlots = value;
+            break;
         case PC_OPT_TRACE_REFILL:
             if (value < -1 || value > 1) return fail(tr, PC_ERR_INVALID_ARGUMENT, "trace refill must be -1 (by scene), 0 or 1");
             tr->optRefill = value;
@@ -882,7 +914,6 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     // the block-local path index, i.e. possibly outside the block's rows: those modes clear the whole frame.
     const bool wholeFrame = !tr->optFixQ4 || dbg;
     const uint32_t rowsY0 = wholeFrame ? 0u : req->block_y, rowsY1 = wholeFrame ? tr->H : req->block_y + req->block_h;
-    if ((rc = clear_for_block(tr, tr->chain[0], tr->traceAcc.p, rowsY0, rowsY1, s))) return rc;
     if (need * 4 > tr->seedsDev.bytes) CU(tr, PC_ERR_ALLOC, tr->seedsDev.alloc(need * 4 + 4096));
     if (need) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(tr->seedsDev.p, seeds, need * 4, cudaMemcpyHostToDevice, s));
     TraceParams hp;
@@ -893,21 +924,31 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     int nc = (tr->optTimers || dbg) ? 1 : tr->optChains;
     if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
     if (dbg) CU(tr, PC_ERR_ALLOC, tr->debugBuf.bytes >= (size_t)tr->W * tr->H * 4 + 16 ? cudaSuccess : tr->debugBuf.alloc((size_t)tr->W * tr->H * 4 + 16));
-    if ((rc = ensure_chains(tr, nc, (size_t)req->frame_w * req->block_h))) return rc;
+    // ---- sample slots: a set of launches carries `slots` samples of a chain (TraceCtl in pc_kernels.cuh): sample k of the
+    // request is traced by chain k % nc in slot (k / nc) % slots.  Automatic: enough slots for ~4 M paths per launch.
+    const size_t blockRays = (size_t)req->frame_w * req->block_h;
+    int slots = tr->optSlots > 0 ? tr->optSlots : (int)((4u << 20) / (blockRays ? blockRays : 1));
+    if (slots > MAX_SLOTS) slots = MAX_SLOTS;
+    if (slots < 1 || dbg || tr->optPackets || tr->optRefOrder) slots = 1;
+    if (slots > MAX_SLOTS) slots = MAX_SLOTS;
+    while (slots > 1 && (uint32_t)(nc * slots) > spp) slots--;
+    while (slots > 1 && blockRays * (size_t)slots >= (1u << 24)) slots--;  // path indices travel as floats... per slot, but ray counts stay below 2^31
+    if ((rc = ensure_chains(tr, nc, blockRays, slots))) return rc;
     static const uint32_t kChainIndex[MAX_CHAINS] = {0, 1, 2, 3, 4, 5, 6, 7};
+    for (int c = 0; c < nc; c++)
+        for (int sl = 0; sl < slots; sl++) {
+            void *acc = c == 0 && sl == 0 ? tr->traceAcc.p : tr->chain[c].accs[sl].p;
+            if ((rc = clear_for_block(tr, tr->chain[c].dirtyY0[sl], tr->chain[c].dirtyY1[sl], acc, rowsY0, rowsY1, s))) return rc;
+        }
     for (int c = 0; c < nc; c++) {
         // reset the persistent part of the control block, keep the three ray counters
         char *ctl = (char *)tr->chain[c].ctl.p;
         CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + offsetof(TraceCtl, nextSample), 0, sizeof(TraceCtl) - offsetof(TraceCtl, nextSample), s));
         // ... except the occlusion-ray counter: the first k_primary of this call must find no rays left over (see k_primary)
         CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl + 2 * sizeof(int), 0, sizeof(int), s));
-        if (c > 0) {
-            CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl + offsetof(TraceCtl, nextSample), &kChainIndex[c], 4, cudaMemcpyHostToDevice, s));
-            if ((rc = clear_for_block(tr, tr->chain[c], tr->chain[c].acc.p, rowsY0, rowsY1, s))) return rc;
-        }
+        if (c > 0) CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl + offsetof(TraceCtl, nextSample), &kChainIndex[c], 4, cudaMemcpyHostToDevice, s));
     }
     uint64_t launches = 2;
-    uint64_t perSampleLaunches = 0;
     CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStart, s));
     if (spp > 0) {
         tr->timerClass.clear();
@@ -916,25 +957,29 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
             for (; done < spp; done++) {
                 dbg->capture = done + 1 == spp;
                 dbg->sampleIndex = done;
-                record_sample(tr, tr->chain[0], *req, 1u, &perSampleLaunches, dbg);
+                uint64_t L = 0;
+                record_sample(tr, tr->chain[0], *req, 1u, 1u, 1u, &L, dbg);
+                launches += L;
             }
             if (cudaGetLastError() != cudaSuccess) {
                 tr->dead = true;
                 return fail(tr, PC_ERR_KERNEL, "debug stage launch failed");
             }
         }
-        if (tr->optGraph && !tr->optTimers && !dbg && spp >= (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc)) {
+        const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc * slots);  // samples per replay of the captured graph
+        if (tr->optGraph && !tr->optTimers && !dbg && spp >= perGraph) {
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
             key.counters = tr->optCounters; key.packets = tr->optPackets; key.reforder = tr->optRefOrder; key.fixq4 = tr->optFixQ4;
-            key.chains = nc; key.fuse = tr->optFuse; key.sort = tr->optSort; key.defer = tr->optDeferOcc; key.refill = tr->refillNow ? 1 : 0; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
+            key.chains = nc; key.slots = slots; key.fuse = tr->optFuse; key.sort = tr->optSort; key.defer = tr->optDeferOcc; key.refill = tr->refillNow ? 1 : 0; memcpy(&key.scene, &tr->sc, sizeof(DScene)); key.seedsPtr = tr->seedsDev.p;
             if (!tr->graphExec || !(key == tr->graphKey)) {
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;
                 uint32_t perChain[MAX_CHAINS] = {};
-                for (int c = 0; c < nc; c++) perChain[c] = GRAPH_SAMPLES_PER_CHAIN;
+                for (int c = 0; c < nc; c++) perChain[c] = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * slots);
+                tr->launchesPerSample = 0;  // launches of one replay
                 CU(tr, PC_ERR_KERNEL, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-                int bad = enqueue_chains(tr, *req, nc, perChain, &tr->launchesPerSample);
+                int bad = enqueue_chains(tr, *req, nc, slots, perChain, &tr->launchesPerSample);
                 cudaError_t ce = cudaStreamEndCapture(s, &graph);
                 if (bad || ce != cudaSuccess) {
                     if (graph) cudaGraphDestroy(graph);
@@ -952,29 +997,36 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
                 // that balances blocks by Stats() must not see it as render time
                 CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStart, s));
             }
-            perSampleLaunches = tr->launchesPerSample;
-            const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc);
-            for (; done + perGraph <= spp; done += perGraph) CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
+            for (; done + perGraph <= spp; done += perGraph) {
+                CU(tr, PC_ERR_KERNEL, cudaGraphLaunch(tr->graphExec, s));
+                launches += tr->launchesPerSample;
+            }
         }
         const bool flush = defer_last_occlusion(tr, dbg != nullptr);
         if (done < spp || flush) {  // the remainder (or everything, without graphs): same chain assignment, direct launches
+            // sample k -> chain k % nc, slot (k / nc) % slots: what is left is `rounds` of nc * slots samples and a tail
             uint32_t perChain[MAX_CHAINS] = {};
             for (uint32_t i = done; i < spp; i++) perChain[i % (uint32_t)nc]++;
-            if (enqueue_chains(tr, *req, nc, perChain, &perSampleLaunches, flush, &launches)) {
+            if (enqueue_chains(tr, *req, nc, slots, perChain, &launches, flush, &launches)) {
                 tr->dead = true;
                 return fail(tr, PC_ERR_KERNEL, "kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
         }
         // chains > 0 accumulated into their own buffers: add them in chain order, the block's rows only, one launch
-        if (nc > 1) {
+        if (nc * slots > 1) {
             ChainAccs ca;
-            ca.n = nc - 1;
-            for (int c = 1; c < nc; c++) ca.src[c - 1] = (const float4 *)tr->chain[c].acc.p;
+            ca.n = 0;
+            for (int c = 0; c < nc; c++)
+                for (int sl = 0; sl < slots; sl++)
+                    if (c || sl) ca.src[ca.n++] = (const float4 *)tr->chain[c].accs[sl].p;
             const size_t off = (size_t)tr->W * rowsY0, cnt = (size_t)tr->W * (rowsY1 - rowsY0);
             k_merge_chains<<<grid_for(cnt, 256, tr->prop.multiProcessorCount * 8), 256, 0, s>>>((float4 *)tr->traceAcc.p, ca, off, cnt);
             launches++;
         }
         tr->lastChain = (int)((spp - 1) % (uint32_t)nc);
+        tr->lastSlot = (int)(((spp - 1) / (uint32_t)nc) % (uint32_t)slots);
+        tr->lastSlotPaths = (uint32_t)blockRays;
+        tr->lastBounces = req->num_bounces;
     }
     CU(tr, PC_ERR_KERNEL, cudaEventRecord(tr->evStop, s));
     CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(s));
@@ -997,7 +1049,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     st.device_time_ns = (uint64_t)((double)ms * 1e6);
     st.query_rays = hc.stats[ST_QUERY_RAYS];
     st.occlusion_rays = hc.stats[ST_OCCLUSION_RAYS];
-    st.kernel_launches = launches + perSampleLaunches * spp + (dbg ? dbg->launches : 0);
+    st.kernel_launches = launches + (dbg ? dbg->launches : 0);
     st.nodes_tested = hc.stats[ST_NODES];
     st.tris_tested = hc.stats[ST_TRIS];
     st.instances_entered = hc.stats[ST_INSTANCES];
@@ -1270,17 +1322,34 @@ int pc_read_buffer(pc_tracer *tr, int which, void *dst, uint64_t bytes) {
     const void *src = nullptr;
     size_t have = 0;
     const Chain &lc = tr->chain[tr->lastChain < tr->nChains ? tr->lastChain : 0];
+    // per-sample state: the buffers of the chain AND SLOT that traced the LAST sample (what the reference's single set would
+    // hold).  A slot's rays start at base[k][slot] of the flat buffers (TraceCtl), its paths at slot * paths-per-slot.
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    TraceCtl hc;
+    memset(&hc, 0, sizeof(hc));
+    if (lc.ctl.p) CU(tr, PC_ERR_COPY_TO_HOST, cudaMemcpy(&hc, lc.ctl.p, sizeof(hc), cudaMemcpyDeviceToHost));
+    const int sl = tr->lastSlot < MAX_SLOTS ? tr->lastSlot : 0;
+    const int aLast = (int)((tr->lastBounces - 1u) & 1u);  // rays[aLast] is what the last closest-hit launch traced
+    int32_t counters[3] = {0, 0, 0};
+    auto slice = [&](const DevBuf &b, size_t elem, size_t firstElem) {
+        const size_t off = firstElem * elem;
+        src = off <= b.bytes ? (const char *)b.p + off : nullptr;
+        have = off <= b.bytes ? b.bytes - off : 0;
+    };
     switch (which) {
-        // per-sample state: the buffers of the chain that traced the LAST sample (what the reference's single set would hold)
-        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: src = lc.rays[which].p; have = lc.rays[which].bytes; break;
-        case PC_BUF_PATHS: src = lc.paths.p; have = lc.paths.bytes; break;
-        case PC_BUF_HIT_FLAGS: src = lc.hitFlags.p; have = lc.hitFlags.bytes; break;
-        case PC_BUF_INTERSECTIONS: src = lc.hits.p; have = lc.hits.bytes; break;
-        case PC_BUF_EMISSIVE_SAMPLES: src = lc.emSamples.p; have = lc.emSamples.bytes; break;
+        case PC_BUF_RAYS0: case PC_BUF_RAYS1: case PC_BUF_RAYS2: slice(lc.rays[which], 32, hc.base[which][sl]); break;
+        case PC_BUF_PATHS: slice(lc.paths, 32, (size_t)sl * tr->lastSlotPaths); break;
+        case PC_BUF_HIT_FLAGS: slice(lc.hitFlags, 4, hc.base[aLast][sl]); break;
+        case PC_BUF_INTERSECTIONS: slice(lc.hits, 32, hc.base[aLast][sl]); break;
+        case PC_BUF_EMISSIVE_SAMPLES: slice(lc.emSamples, 16, hc.base[2][sl]); break;
         case PC_BUF_TRACE_ACCUMULATOR: src = tr->traceAcc.p; have = tr->traceAcc.bytes; break;
         case PC_BUF_FRAME_ACCUMULATOR: src = tr->frameAcc.p; have = tr->frameAcc.bytes; break;
         case PC_BUF_FRAME_BUFFER: src = tr->frameBuf.p; have = tr->frameBuf.bytes; break;
-        case PC_BUF_RAY_COUNTERS: src = lc.ctl.p; have = 12; break;
+        case PC_BUF_RAY_COUNTERS:  // the slot's share of the three counters
+            for (int k = 0; k < 3; k++) counters[k] = (int32_t)(hc.base[k][sl + 1] - hc.base[k][sl]);
+            if (bytes > 12) return fail(tr, PC_ERR_INVALID_ARGUMENT, "the ray counters are 12 bytes");
+            memcpy(dst, counters, bytes);
+            return 0;
         default: return fail(tr, PC_ERR_INVALID_ARGUMENT, "unknown buffer %d", which);
     }
     // per-sample state is sized by the largest block traced (the reference's is frame sized): what lies beyond it was never
@@ -1309,15 +1378,23 @@ int pc_debug_intersect(pc_tracer *tr, const void *rays, uint32_t n, int mode, ui
     TraceCtl *ctl = (TraceCtl *)c0.ctl.p;
     CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(c0.rays[0].p, rays, (size_t)n * 32, cudaMemcpyHostToDevice, s));
     CU(tr, PC_ERR_KERNEL, cudaMemsetAsync(ctl, 0, sizeof(TraceCtl), s));
-    int cnt[3] = {(int)n, 0, (int)n};
-    CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl, cnt, 12, cudaMemcpyHostToDevice, s));
+    {   // one slot holding all n rays, in rays[0] (closest hit) and as rays[2] (any hit)
+        TraceCtl hc;
+        memset(&hc, 0, sizeof(hc));
+        hc.numRays[0] = (int)n; hc.numRays[2] = (int)n;
+        hc.nSlots = 1; hc.slotStride = 1; hc.slotPaths = n;
+        for (int k = 1; k <= MAX_SLOTS; k++) { hc.base[0][k] = n; hc.base[2][k] = n; }
+        CU(tr, PC_ERR_COPY_TO_DEVICE, cudaMemcpyAsync(ctl, &hc, sizeof(hc), cudaMemcpyHostToDevice, s));
+        CU(tr, PC_ERR_COPY_TO_DEVICE, cudaStreamSynchronize(s));  // hc lives on this stack frame
+    }
+    tr->lastChain = 0; tr->lastSlot = 0; tr->lastSlotPaths = n; tr->lastBounces = 1;
     const int pg = tr->persistentGrid;
     if (mode == 0) {
         if (tr->optRefOrder) k_query<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0, nullptr);
         else k_query<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, 0, 0, nullptr);
     } else if (mode == 1) {
-        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0, nullptr);
-        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, nullptr, c0.fb.hitFlags, ctl, 0, nullptr);
+        if (tr->optRefOrder) k_occlusion<true, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, c0.fb, 0, c0.fb.hitFlags, ctl, 0, nullptr);
+        else k_occlusion<false, false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.paths, c0.fb.emissiveSamples, c0.fb, 0, c0.fb.hitFlags, ctl, 0, nullptr);
     } else if (mode == 2) {
         k_debug_packet<false><<<pg, TRAV_BLOCK, 0, s>>>(tr->sc, c0.fb.rays[0], c0.fb.hitFlags, c0.fb.hits, ctl, n, 0);
     } else {

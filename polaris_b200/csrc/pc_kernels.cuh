@@ -58,12 +58,24 @@ enum StatIdx {
 
 // Device control block.  [persist] survives a whole pc_trace call, [sample] is zeroed by
 // k_begin_sample.
+// Sample slots.  The samples of a block request are independent, and at the BASELINE frame sizes ONE sample does not fill
+// the machine (config 2's scene: 3.8 Grays/s at 1 Mpx per launch, 4.2 at 4 Mpx, profiles/size_effect_r02.txt), so a launch
+// carries up to MAX_SLOTS samples at once: slot s of a batch is the sample curSample + s * slotStride.  The ray buffers
+// stay FLAT -- slot 0's rays, then slot 1's, ... -- and because compaction is stable that grouping survives every bounce;
+// all a kernel needs is where each slot starts in each ray buffer (base[k][s]) to recover, for ray i of rays[k], its slot,
+// its slot-local index (the RNG key of pt_integrator.cl:81 -- results are bit-identical to tracing the samples one by
+// one), its path record (paths[slot * slotPaths + pathIndex]) and its accumulator (FrameBufs::slotAcc[slot]).
+constexpr int MAX_SLOTS = 8;
+constexpr int MAX_CHAINS_X_SLOTS = 64;
 struct TraceCtl {
-    int numRays[3];            // [persist] the reference's three ray counters (buffers.go:69)
+    int numRays[3];            // [persist] the reference's three ray counters (buffers.go:69), over all slots
     uint32_t nextSample;       // [persist]
-    uint32_t curSample;        // [persist] index of the sample being traced
-    uint32_t pad0[3];
+    uint32_t curSample;        // [persist] index of slot 0's sample of the batch being traced
+    uint32_t nSlots;           // slots of the batch being traced (k_begin_sample)
+    uint32_t slotStride;       // sample-index distance between consecutive slots (= number of chains)
+    uint32_t slotPaths;        // paths per slot = FrameW * BlockH (k_primary)
     unsigned long long stats[ST_COUNT];  // [persist]
+    uint32_t base[3][MAX_SLOTS + 1];     // first ray of every slot in rays[k]; entries of unused slots hold numRays[k]
     uint32_t queueHead[2 * MAX_BOUNCES + 2];  // [sample] work-queue heads, one per traversal launch
     uint32_t ticket[MAX_BOUNCES];             // [sample] block tickets of the shade launches
 };
@@ -86,8 +98,24 @@ struct FrameBufs {
     uint32_t *hitFlags;
     HitRec *hits;
     float4 *emissiveSamples;
-    float4 *traceAcc;
+    float4 *traceAcc;             // == slotAcc[0]
     uint32_t *permOcc, *permInd;  // traversal order of rays[2] / of the next bounce's rays (PC_OPT_SORT_RAYS)
+    float4 *slotAcc[MAX_SLOTS];   // one accumulator per sample slot: two samples of a batch may hit the same pixel at once
+};
+
+// slot of ray i given the slots' first rays b[0..MAX_SLOTS] (unused slots start at the total: never selected)
+__device__ __forceinline__ uint32_t slotOf(const uint32_t *b, uint32_t i) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 1; k < MAX_SLOTS; k++) s += i >= b[k] ? 1u : 0u;
+    return s;
+}
+struct SlotBases {
+    uint32_t b[MAX_SLOTS + 1];
+    __device__ __forceinline__ void load(const uint32_t *src) {
+#pragma unroll
+        for (int k = 0; k <= MAX_SLOTS; k++) b[k] = src[k];
+    }
 };
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
@@ -147,12 +175,15 @@ __device__ __forceinline__ uint32_t next_unit_adaptive(uint32_t *head, uint32_t 
 
 #ifndef PC_SHADE_TU  // non-template kernels live in the exact-arithmetic translation unit only (pc_host.cu)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords, uint32_t sampleStride) {
+__global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t statusWords, uint32_t sampleAdvance, uint32_t nSlots,
+                               uint32_t slotStride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    if (i == 0) {  // a chain traces every sampleStride-th sample of the block request
+    if (i == 0) {  // a chain traces batches of nSlots samples: curSample, curSample + slotStride, ...
         ctl->curSample = ctl->nextSample;
-        ctl->nextSample = ctl->nextSample + sampleStride;
+        ctl->nextSample = ctl->nextSample + sampleAdvance;
+        ctl->nSlots = nSlots;
+        ctl->slotStride = slotStride;
     }
     if (i < 2 * MAX_BOUNCES + 2) ctl->queueHead[i] = 0;
     if (i < MAX_BOUNCES) ctl->ticket[i] = 0;
@@ -452,13 +483,17 @@ __device__ __forceinline__ int traverse_packet(const DScene &sc, uint2 *stack, b
 struct PrimarySource {
     FrameBufs fb;
     CameraParams cam;
-    uint32_t frameW, blockY, randSeed;
+    uint32_t frameW, blockY, slotPaths;
+    const uint32_t *seeds;      // camera seed of slot s at seeds[(curSample + s * slotStride) * seedsPerSample]
+    uint32_t curSample, slotStride, seedsPerSample;
     __device__ __forceinline__ void load(uint32_t index, float3 &o, float3 &d, float &tmax) const {
-        const uint32_t gx = index % frameW, gy = index / frameW;
+        const uint32_t slot = index / slotPaths, local = index - slot * slotPaths;  // ray index == slot * slotPaths + path index
+        const uint32_t gx = local % frameW, gy = local / frameW;
+        const uint32_t randSeed = __ldg(seeds + (size_t)(curSample + slot * slotStride) * seedsPerSample);
         d = primaryRayDir(cam, gx, gy, blockY, randSeed);
         o = cam.eye;
         tmax = FLT_MAX;
-        st_ray(fb.rays[0] + index, f4(cam.eye, FLT_MAX), f4(d, (float)index));  // rayNew (util/ray.cl:13-16)
+        st_ray(fb.rays[0] + index, f4(cam.eye, FLT_MAX), f4(d, (float)local));  // rayNew (util/ray.cl:13-16)
         // pathNew (util/path.cl:13-17)
         __stcs(&fb.paths[index].throughput, make_float4(1.0f, 1.0f, 1.0f, 0.0f));
         __stcs(&fb.paths[index].meta, make_uint4((gy + blockY) * frameW + gx, 0u, 0u, 0u));
@@ -473,15 +508,19 @@ struct OcclusionSink {
     const Ray *rays;
     const PathRec *paths;
     const float4 *emissiveSamples;
-    float4 *acc;
+    float4 *const *slotAcc;   // the slots' accumulators (shared memory); null: flags only (test hook)
     uint32_t *hitFlags;
     uint32_t unocc;
+    const uint32_t *base;     // slots' first rays in `rays` (shared memory)
+    uint32_t slotPaths;
     __device__ __forceinline__ void store(uint32_t i, int hit, const Trav &) {
         if (hitFlags) hitFlags[i] = (uint32_t)hit;
-        if (!hit && acc) {
+        if (!hit && slotAcc) {
+            const uint32_t slot = slotOf(base, i);
             const uint32_t pathIndex = (uint32_t)__ldcs(&rays[i].dir.w);  // rayGetPathIndex (util/ray.cl:26-28)
-            const uint32_t pixel = paths[pathIndex].meta.x;
+            const uint32_t pixel = paths[(size_t)slot * slotPaths + pathIndex].meta.x;
             const float4 s = __ldcs(emissiveSamples + i);
+            float4 *acc = slotAcc[slot];
             float4 c = acc[pixel];
             c.x += s.x; c.y += s.y; c.z += s.z;
             acc[pixel] = c;
@@ -489,6 +528,16 @@ struct OcclusionSink {
         }
     }
 };
+// the slots' first rays of rays[k] and the slots' accumulators, staged in shared memory once per CTA (dynamic indexing
+// of a kernel parameter would put it in local memory); call before the first use, syncs the CTA
+__device__ __forceinline__ void loadSlotBases(uint32_t *dst, float4 **accDst, const TraceCtl *ctl, int k, const FrameBufs &fb) {
+    if (threadIdx.x <= MAX_SLOTS) dst[threadIdx.x] = ctl->base[k][threadIdx.x];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < MAX_SLOTS; q++) accDst[q] = fb.slotAcc[q];
+    }
+    __syncthreads();
+}
 
 // MODE 0: per-ray traversal, 1: warp packets over 8x4 pixel tiles, 2: reference-order per-ray.
 // occSlot >= 0 (MODE 0 only): the launch ALSO drains the any-hit queue the PREVIOUS sample of this chain left behind -- its last
@@ -503,24 +552,32 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(D
     __shared__ uint2 s_stack[MODE == 1 ? (TRAV_BLOCK / 32) * PC_STACK_SIZE : 1];
     const CameraParams cam = params->cam;
     const uint32_t frameW = params->frameW, blockY = params->blockY, blockH = params->blockH;
-    const uint32_t n = frameW * blockH;
-    const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample];
+    const uint32_t n = frameW * blockH;                       // paths per slot
+    const uint32_t nSlots = MODE == 0 ? ctl->nSlots : 1u;      // packets / the literal walk trace one sample per launch
+    const uint32_t total = n * nSlots;
+    const uint32_t curSample = ctl->curSample, slotStride = ctl->slotStride;
+    const uint32_t randSeed = seeds[(size_t)curSample * seedsPerSample];
+    __shared__ uint32_t s_base2[MAX_SLOTS + 1];
+    __shared__ float4 *s_acc[MAX_SLOTS];
+    if (occSlot >= 0) loadSlotBases(s_base2, s_acc, ctl, 2, fb);  // the previous batch's occlusion rays
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ctl->numRays[0] = (int)n;  // camera.cl:24-26
-        atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)n);
+        ctl->numRays[0] = (int)total;  // camera.cl:24-26
+        ctl->slotPaths = n;
+        for (uint32_t k = 0; k <= MAX_SLOTS; k++) ctl->base[0][k] = (k < nSlots ? k : nSlots) * n;
+        atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)total);
     }
     TravStats st{0, 0, 0};
     uint32_t missed = 0;
     if (MODE == 0) {
         PC_TRAV_STACK(stack);
-        PrimarySource src{fb, cam, frameW, blockY, randSeed};
+        PrimarySource src{fb, cam, frameW, blockY, n, seeds, curSample, slotStride, seedsPerSample};
         HitSink<COUNT> sink{fb.hitFlags, fb.hits, 0u};
-        trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], n, st, src, sink);
+        trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], total, st, src, sink);
         missed = sink.missed;
         if (occSlot >= 0) {
             const uint32_t nO = (uint32_t)ctl->numRays[2];
             if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
-            OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, 0u};
+            OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, s_acc, nullptr, 0u, s_base2, n};
             RaySource osrc{fb.rays[2]};
             trace_queue<true, COUNT>(sc, stack, &ctl->queueHead[occSlot], nO, st, osrc, osink, sorted ? fb.permOcc : nullptr);
             if (COUNT) warp_add_stat(ctl, ST_UNOCCLUDED, osink.unocc);
@@ -617,12 +674,15 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_query(DScene
 
 template <bool REFERENCE, bool COUNT>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DScene sc, const Ray *rays, const PathRec *paths,
-                                                         const float4 *emissiveSamples, float4 *acc, uint32_t *hitFlags,
+                                                         const float4 *emissiveSamples, FrameBufs fbAcc, int accumulate, uint32_t *hitFlags,
                                                          TraceCtl *ctl, int queueSlot, const uint32_t *perm) {
     const uint32_t n = (uint32_t)ctl->numRays[2];
+    __shared__ uint32_t s_base2[MAX_SLOTS + 1];
+    __shared__ float4 *s_acc[MAX_SLOTS];
+    loadSlotBases(s_base2, s_acc, ctl, 2, fbAcc);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)n);
     TravStats st{0, 0, 0};
-    OcclusionSink<COUNT> sink{rays, paths, emissiveSamples, acc, hitFlags, 0u};
+    OcclusionSink<COUNT> sink{rays, paths, emissiveSamples, accumulate ? s_acc : nullptr, hitFlags, 0u, s_base2, ctl->slotPaths};
     if (!REFERENCE) {
         PC_TRAV_STACK(stack);
         RaySource src{rays};
@@ -660,6 +720,9 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_OCC_MIN_BLOCKS) k_occlusion(DSc
 template <bool COUNT, bool REFILL>
 __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene sc, FrameBufs fb, TraceCtl *ctl, int a, int queueSlot, int sorted) {
     const uint32_t nQ = (uint32_t)ctl->numRays[a], nO = (uint32_t)ctl->numRays[2];
+    __shared__ uint32_t s_base2[MAX_SLOTS + 1];
+    __shared__ float4 *s_acc[MAX_SLOTS];
+    loadSlotBases(s_base2, s_acc, ctl, 2, fb);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&ctl->stats[ST_QUERY_RAYS], (unsigned long long)nQ);
         atomicAdd(&ctl->stats[ST_OCCLUSION_RAYS], (unsigned long long)nO);
@@ -672,7 +735,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_TRAV_MIN_BLOCKS) k_trace(DScene
     trace_queue<false, COUNT, REFILL>(sc, stack, &ctl->queueHead[queueSlot], nQ, st, qsrc, qsink, sorted ? fb.permInd : nullptr);
     // ... then the any-hit queue, whose short walks make the launch's tail
     RaySource osrc{fb.rays[2]};
-    OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, fb.traceAcc, nullptr, 0u};
+    OcclusionSink<COUNT> osink{fb.rays[2], fb.paths, fb.emissiveSamples, s_acc, nullptr, 0u, s_base2, ctl->slotPaths};
     trace_queue<true, COUNT, REFILL>(sc, stack, &ctl->queueHead[queueSlot + 1], nO, st, osrc, osink, sorted ? fb.permOcc : nullptr);
     const uint32_t missed = qsink.missed, unocc = osink.unocc;
     if (COUNT) {
@@ -794,6 +857,8 @@ struct ShadeShared {
     uint32_t groupOcc[SHADE_GROUPS], groupInd[SHADE_GROUPS];  // per 32-slot group: counts, then exclusive offsets
     uint32_t binOcc[SORT_BINS], binInd[SORT_BINS];  // traversal-order sort of the emitted rays: per-key counts, then first positions
     uint32_t tile, occBase, indBase, nextChunk, activeChunks;
+    uint32_t baseA[MAX_SLOTS + 1];   // first ray of every sample slot in rays[a]
+    float4 *acc[MAX_SLOTS];          // the slots' accumulators
 };
 
 // k_shade is compiled in its own translation unit (pc_shade.cu) so that it can carry its own floating-point flags:
@@ -831,8 +896,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
     if (n == 0 && blockIdx.x == 0 && tid == 0) {  // resources.go:230-238: both counters reset
         ctl->numRays[2] = 0;
         ctl->numRays[1 - a] = 0;
+        for (int k = 0; k <= MAX_SLOTS; k++) { ctl->base[2][k] = 0u; ctl->base[1 - a][k] = 0u; }
     }
-    const uint32_t randSeed = seeds[(size_t)ctl->curSample * seedsPerSample + 1 + bounce];
+    const uint32_t curSample = ctl->curSample, slotStride = ctl->slotStride, slotPaths = ctl->slotPaths;
+    if (tid <= MAX_SLOTS) sh.baseA[tid] = ctl->base[a][tid];
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < MAX_SLOTS; q++) sh.acc[q] = fb.slotAcc[q];
+    }
     uint32_t shaded = 0;
     for (;;) {
         __syncthreads();  // the previous tile's shared state is no longer in use
@@ -902,30 +973,40 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             so.wantOcc = false; so.wantInd = false;
             const float4 rd = __ldcs(&fb.rays[a][i].dir);
             const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
+            // the ray's sample slot: its path records, its accumulator, its seed and its index WITHIN the sample (the
+            // reference's get_global_id(0), the RNG key of pt_integrator.cl:81)
+            const uint32_t sslot = slotOf(sh.baseA, i);
+            const uint32_t pathAt = sslot * slotPaths + pathIndex;
             const uint32_t tri = sh.hitTri[slot];
             if (tri == 0xFFFFFFFFu) {
                 if (sc.sceneDiffuseMat != -1) {  // pipeline.go:134-143
                     float3 kd = shadeMiss(sc, xyz(rd));
-                    PathRec p = ld_path(fb.paths + pathIndex);
+                    PathRec p = ld_path(fb.paths + pathAt);
                     float3 add = bounce == 0 ? kd : xyz(p.throughput) * kd;
-                    float4 cc = fb.traceAcc[p.meta.x];
+                    float4 *acc = sh.acc[sslot];
+                    float4 cc = acc[p.meta.x];
                     cc.x += add.x; cc.y += add.y; cc.z += add.z;
-                    fb.traceAcc[p.meta.x] = cc;
+                    acc[p.meta.x] = cc;
                 }
                 continue;
             }
             shaded++;
-            const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
-            const PathRec p = ld_path(fb.paths + pathIndex);
-            shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, i, bounce, minBouncesForRR, randSeed, so);
-            if (so.flagsChanged) fb.paths[pathIndex].meta.y = so.pathFlags;
-            if (so.accum) {
-                const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
-                float4 cc = fb.traceAcc[dst];
-                cc.x += so.accumAdd.x; cc.y += so.accumAdd.y; cc.z += so.accumAdd.z;
-                fb.traceAcc[dst] = cc;
+            {
+                const uint32_t rayIndex = i - sh.baseA[sslot];
+                const uint32_t randSeed = __ldg(seeds + (size_t)(curSample + sslot * slotStride) * seedsPerSample + 1 + bounce);
+                const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
+                const PathRec p = ld_path(fb.paths + pathAt);
+                shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, rayIndex, bounce, minBouncesForRR, randSeed, so);
+                if (so.accum) {
+                    const uint32_t dst = fixQ4 ? p.meta.x : pathIndex;  // pt_integrator.cl:106, SURVEY Q4
+                    float4 *acc = sh.acc[sslot];
+                    float4 cc = acc[dst];
+                    cc.x += so.accumAdd.x; cc.y += so.accumAdd.y; cc.z += so.accumAdd.z;
+                    acc[dst] = cc;
+                }
             }
-            if (so.wantInd) fb.paths[pathIndex].throughput = f4(so.newThroughput, 0.0f);
+            if (so.flagsChanged) fb.paths[pathAt].meta.y = so.pathFlags;
+            if (so.wantInd) fb.paths[pathAt].throughput = f4(so.newThroughput, 0.0f);
             // ---- 3. stage at the ORIGINAL slot
             sh.flags[slot] = (uint8_t)((so.wantOcc ? 1u : 0u) | (so.wantInd ? 2u : 0u));
             sh.pathIndexF[slot] = rd.w;
@@ -1000,6 +1081,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 if (tile == nTiles - 1) {  // the last tile publishes the queue lengths
                     ctl->numRays[2] = (int)(occBase + occTot);
                     ctl->numRays[1 - a] = (int)(indBase + indTot);
+                    ctl->base[2][0] = 0u;
+                    ctl->base[1 - a][0] = 0u;
+                    for (int k = 1; k <= MAX_SLOTS; k++)  // slots that start at the end of the input (empty / unused ones)
+                        if (sh.baseA[k] >= n) { ctl->base[2][k] = occBase + occTot; ctl->base[1 - a][k] = indBase + indTot; }
                     if (COUNT) {
                         atomicAdd(&ctl->stats[ST_OCC_EMITTED], (unsigned long long)(occBase + occTot));
                         atomicAdd(&ctl->stats[ST_IND_EMITTED], (unsigned long long)(indBase + indTot));
@@ -1008,6 +1093,23 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             }
         }
         __syncthreads();
+        // where every sample slot's rays start in the two OUTPUT buffers: stable compaction keeps the slots grouped, so a
+        // slot's first output ray is the output position of its first input ray.  The warp owning that ray's 32-slot group
+        // publishes it.
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < SHADE_RPT; r++) {
+                if ((uint32_t)r >= rpt) break;
+                const uint32_t g = r * SHADE_WARPS + warp;
+                for (int k = 1; k <= MAX_SLOTS; k++) {
+                    const uint32_t B = sh.baseA[k];
+                    if (B >= n || B < base + g * 32u || B >= base + g * 32u + 32u) continue;
+                    const unsigned below = (1u << (B - base - g * 32u)) - 1u;
+                    ctl->base[2][k] = sh.occBase + sh.groupOcc[g] + (uint32_t)__popc(occMask[r] & below);
+                    ctl->base[1 - a][k] = sh.indBase + sh.groupInd[g] + (uint32_t)__popc(indMask[r] & below);
+                }
+            }
+        }
 #pragma unroll
         for (int r = 0; r < SHADE_RPT; r++) {
             if ((uint32_t)r >= rpt) break;
@@ -1082,7 +1184,7 @@ __global__ void k_merge(float4 *__restrict__ dst, const float4 *__restrict__ src
 // the sample chains' accumulators added to the trace accumulator in chain order, ((acc + c1) + c2) + ...: the same
 // float32 sums as one k_merge per chain, in one pass over the block's rows
 struct ChainAccs {
-    const float4 *src[7];
+    const float4 *src[MAX_CHAINS_X_SLOTS];
     int n;
 };
 __global__ void k_merge_chains(float4 *__restrict__ dst, ChainAccs ca, size_t off, size_t n) {

@@ -162,7 +162,8 @@ def test_variants_bit_identical():
                  {"fuse_trace": 1}, {"fuse_trace": 1, "counters": 1}, {"fuse_trace": 1, "use_graph": 0}, {"sort_rays": 1},
                  {"sort_rays": 0}, {"sort_rays": 1, "fuse_trace": 0}, {"sort_rays": 1, "counters": 1, "use_graph": 0},
                  {"defer_occlusion": 0}, {"defer_occlusion": 0, "use_graph": 0}, {"defer_occlusion": 1, "counters": 1},
-                 {"trace_refill": 1}, {"trace_refill": 0}, {"trace_refill": 1, "counters": 1, "sort_rays": 0}):
+                 {"trace_refill": 1}, {"trace_refill": 0}, {"trace_refill": 1, "counters": 1, "sort_rays": 0},
+                 {"sample_slots": 1}, {"sample_slots": 2, "sample_chains": 1}, {"sample_slots": 2, "use_graph": 0}):
         cu = C.cuda_for(sc, w, h, **opts)
         cu.trace(T.make_block_request(w, h, spp=2), seeds)
         acc = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
@@ -212,6 +213,46 @@ def test_refilling_traversal_bit_identical(key, w, h):
                     st["query_rays"], st["occlusion_rays"], st["unoccluded"], st["missed_query_rays"]))
         cu.close()
     assert res[0] == res[1]
+
+
+@pytest.mark.parametrize("key,w,h", [("c2", 128, 96), ("c4", 160, 96)])
+def test_sample_slots_bit_identical(key, w, h):
+    """PC_OPT_SAMPLE_SLOTS: S samples per set of launches.  Every sample keeps its own seeds, ray numbering and accumulator,
+    so one chain with S slots groups and orders the samples exactly like S chains with one slot each: accumulator, ray
+    totals, and the last sample's per-sample state (rays, paths, hit records, counters) are bit-identical, for full batches,
+    a partial last batch and a block that does not start at row 0."""
+    sc = C.small_scene(key, w, h)
+    for spp, by, bh in ((8, 0, h), (11, 16, 64), (3, 8, 40)):
+        seeds = T.splitmix_seeds(14, spp * 6)
+        for S in (2, 4):
+            res = []
+            for chains, slots in ((S, 1), (1, S)):
+                cu = C.cuda_for(sc, w, h, sample_chains=chains, sample_slots=slots, counters=1)
+                cu.trace(T.make_block_request(w, h, block_y=by, block_h=bh, spp=spp), seeds)
+                st = cu.stats().device
+                n = w * bh
+                res.append((cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes(),
+                            cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32).tobytes(),
+                            cu.read_buffer(_lib.BUF_PATHS, n, _lib.PATH_DTYPE).tobytes(),
+                            st["query_rays"], st["occlusion_rays"], st["shaded_hits"], st["unoccluded"], st["missed_query_rays"]))
+                cnt = cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32)
+                res[-1] += (cu.read_buffer(_lib.BUF_RAYS2, n, _lib.RAY_DTYPE)[: cnt[2]].tobytes(),
+                            cu.read_buffer(_lib.BUF_EMISSIVE_SAMPLES, n * 4, np.float32)[: 4 * cnt[2]].tobytes())
+                cu.close()
+            assert res[0] == res[1], f"{key} spp={spp} rows {by}+{bh}: {S} slots differ from {S} chains"
+    # one bounce: the last sample's primary rays and hit records sit in its slot's segment
+    spp = 3
+    seeds = T.splitmix_seeds(15, spp * 2)
+    out = []
+    for chains, slots in ((1, 1), (1, 3)):
+        cu = C.cuda_for(sc, w, h, sample_chains=chains, sample_slots=slots)
+        cu.trace(T.make_block_request(w, h, spp=spp, num_bounces=1), seeds)
+        n = w * h
+        out.append((cu.read_buffer(_lib.BUF_RAYS0, n, _lib.RAY_DTYPE).tobytes(), cu.read_buffer(_lib.BUF_HIT_FLAGS, n, np.uint32).tobytes(),
+                    cu.read_buffer(_lib.BUF_INTERSECTIONS, n, _lib.INTERSECTION_DTYPE)["tri_index"].tobytes(),
+                    cu.read_buffer(_lib.BUF_RAY_COUNTERS, 3, np.int32).tobytes()))
+        cu.close()
+    assert out[0][3] == out[1][3] and out[0][0] == out[1][0] and out[0][1] == out[1][1]
 
 
 def test_sample_chains_equivalent():
@@ -522,7 +563,8 @@ def test_debug_stages_vs_oracle(key, w, h):
     # normals stage's matSelectNode changes no path state)
     if key == "c2":
         acc_dbg = cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes()
-        cu.set_option(_lib.OPT_SAMPLE_CHAINS, 1)
+        cu.set_option(_lib.OPT_SAMPLE_CHAINS, 1)  # one chain, one slot: the samples accumulate one after the other, like the debug pass
+        cu.set_option(_lib.OPT_SAMPLE_SLOTS, 1)
         cu.trace(T.make_block_request(w, h, spp=spp, num_bounces=nb), seeds)
         assert cu.read_buffer(_lib.BUF_TRACE_ACCUMULATOR, w * h * 4, np.float32).tobytes() == acc_dbg
     # a subset of stages, a row block, too small a frame buffer

@@ -18,6 +18,6 @@ for c in c2 c5 c3 c4; do
   for v in default refill refill20 refill26s4; do
     lib=""; [ "$v" != default ] && lib=$PWD/ab_$v.so
     echo "== $c $v"
-    POLARIS_CUDA_LIB=$lib timeout 600 python bench.py --config $c --steps 2 --warmup 2 --spp 64 --no-cpu 2>&1 | grep -E "timed|kernel classes|Error|error" | sed -e 's/"alg_GBps": [0-9.]*//g' -e 's/"launches_per_sample": [0-9]*, //g' -e 's/"mean_avg_us": [0-9.]*, //g' | cut -c1-400
+    POLARIS_CUDA_LIB=$lib timeout 600 python bench.py --config $c --steps 2 --warmup 2 --spp 64 --no-cpu 2>&1 | grep -E "timed|kernel classes|Error|error" | sed -e 's/"alg_GBps": [0-9.]*//g' -e 's///g' -e 's/"mean_avg_us": [0-9.]*, //g' | cut -c1-400
   done
 done 2>&1 | tee gpurun_out/ab_r02d.txt
