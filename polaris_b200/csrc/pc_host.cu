@@ -925,9 +925,9 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
     if (dbg) CU(tr, PC_ERR_ALLOC, tr->debugBuf.bytes >= (size_t)tr->W * tr->H * 4 + 16 ? cudaSuccess : tr->debugBuf.alloc((size_t)tr->W * tr->H * 4 + 16));
     // ---- sample slots: a set of launches carries `slots` samples of a chain (TraceCtl in pc_kernels.cuh): sample k of the
-    // request is traced by chain k % nc in slot (k / nc) % slots.  Automatic: enough slots for ~4 M paths per launch.
+    // request is traced by chain k % nc in slot (k / nc) % slots.  Automatic: enough slots for ~8 M paths per launch (profiles/ab_r02g.txt).
     const size_t blockRays = (size_t)req->frame_w * req->block_h;
-    int slots = tr->optSlots > 0 ? tr->optSlots : (int)((4u << 20) / (blockRays ? blockRays : 1));
+    int slots = tr->optSlots > 0 ? tr->optSlots : (int)((8u << 20) / (blockRays ? blockRays : 1));
     if (slots > MAX_SLOTS) slots = MAX_SLOTS;
     if (slots < 1 || dbg || tr->optPackets || tr->optRefOrder) slots = 1;
     if (slots > MAX_SLOTS) slots = MAX_SLOTS;
