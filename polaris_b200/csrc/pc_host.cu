@@ -966,7 +966,10 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
                 return fail(tr, PC_ERR_KERNEL, "debug stage launch failed");
             }
         }
-        const uint32_t perGraph = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * nc * slots);  // samples per replay of the captured graph
+        // batches every chain contributes to one replay of the captured graph: 4 one-sample batches, fewer when a batch
+        // already carries several samples (a 64-spp pass at 4 chains x 8 slots is two replays)
+        const int graphBatches = slots >= 4 ? 1 : (slots >= 2 ? 2 : GRAPH_SAMPLES_PER_CHAIN);
+        const uint32_t perGraph = (uint32_t)(graphBatches * nc * slots);  // samples per replay
         if (tr->optGraph && !tr->optTimers && !dbg && spp >= perGraph) {
             GraphKey key;
             key.nb = req->num_bounces; key.rr = req->min_bounces_for_rr;
@@ -976,7 +979,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
                 drop_graph(tr);
                 cudaGraph_t graph = nullptr;
                 uint32_t perChain[MAX_CHAINS] = {};
-                for (int c = 0; c < nc; c++) perChain[c] = (uint32_t)(GRAPH_SAMPLES_PER_CHAIN * slots);
+                for (int c = 0; c < nc; c++) perChain[c] = (uint32_t)(graphBatches * slots);
                 tr->launchesPerSample = 0;  // launches of one replay
                 CU(tr, PC_ERR_KERNEL, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
                 int bad = enqueue_chains(tr, *req, nc, slots, perChain, &tr->launchesPerSample);

@@ -229,7 +229,7 @@ __global__ void k_begin_sample(TraceCtl *ctl, unsigned long long *status, size_t
 #define PC_REFILL_AUTO_MIN_NODES 8192   // inner BVH nodes from which the automatic policy switches k_trace to refilling
 #endif
 #ifndef PC_REFILL_THRESHOLD
-#define PC_REFILL_THRESHOLD 20
+#define PC_REFILL_THRESHOLD 16
 #endif
 #ifndef PC_SEARCH_MIN
 #define PC_SEARCH_MIN 8
@@ -858,6 +858,7 @@ struct ShadeShared {
     uint32_t binOcc[SORT_BINS], binInd[SORT_BINS];  // traversal-order sort of the emitted rays: per-key counts, then first positions
     uint32_t tile, occBase, indBase, nextChunk, activeChunks;
     uint32_t baseA[MAX_SLOTS + 1];   // first ray of every sample slot in rays[a]
+    uint32_t seed[MAX_SLOTS];        // the slots' shadeHits seeds of this bounce (pipeline.go:146)
     float4 *acc[MAX_SLOTS];          // the slots' accumulators
 };
 
@@ -898,8 +899,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         ctl->numRays[1 - a] = 0;
         for (int k = 0; k <= MAX_SLOTS; k++) { ctl->base[2][k] = 0u; ctl->base[1 - a][k] = 0u; }
     }
-    const uint32_t curSample = ctl->curSample, slotStride = ctl->slotStride, slotPaths = ctl->slotPaths;
+    const uint32_t slotPaths = ctl->slotPaths;
+    const bool oneSlot = ctl->nSlots <= 1u;  // uniform: no slot lookup per ray
     if (tid <= MAX_SLOTS) sh.baseA[tid] = ctl->base[a][tid];
+    if (tid < MAX_SLOTS) sh.seed[tid] = tid < ctl->nSlots ? seeds[(size_t)(ctl->curSample + tid * ctl->slotStride) * seedsPerSample + 1 + bounce] : 0u;
     if (tid == 0) {
 #pragma unroll
         for (int q = 0; q < MAX_SLOTS; q++) sh.acc[q] = fb.slotAcc[q];
@@ -975,7 +978,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             const uint32_t pathIndex = (uint32_t)rd.w;  // rayGetDirAndPathIndex (util/ray.cl:19-23)
             // the ray's sample slot: its path records, its accumulator, its seed and its index WITHIN the sample (the
             // reference's get_global_id(0), the RNG key of pt_integrator.cl:81)
-            const uint32_t sslot = slotOf(sh.baseA, i);
+            const uint32_t sslot = oneSlot ? 0u : slotOf(sh.baseA, i);
             const uint32_t pathAt = sslot * slotPaths + pathIndex;
             const uint32_t tri = sh.hitTri[slot];
             if (tri == 0xFFFFFFFFu) {
@@ -993,7 +996,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             shaded++;
             {
                 const uint32_t rayIndex = i - sh.baseA[sslot];
-                const uint32_t randSeed = __ldg(seeds + (size_t)(curSample + sslot * slotStride) * seedsPerSample + 1 + bounce);
+                const uint32_t randSeed = sh.seed[sslot];
                 const float4 wuvt = __ldcs(&fb.hits[i].wuvt);
                 const PathRec p = ld_path(fb.paths + pathAt);
                 shadeHit(sc, xyz(rd), xyz(p.throughput), p.meta.y, wuvt, tri, rayIndex, bounce, minBouncesForRR, randSeed, so);
