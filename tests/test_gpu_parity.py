@@ -105,12 +105,21 @@ def test_bxdf_tables(key):
     recs = C.bxdf_records(sc)
     orc, cu = C.oracle_for(sc, 64, 64), C.cuda_for(sc, 64, 64)
     o, g = orc.debug_bxdf(recs), cu.debug_bxdf(recs)
+    mat_type = sc.material_nodes["union1"][recs["mat_node"], 0]  # MaterialNode.Union1[0] = node type (bxdf.go:6-17)
     for f in ("sample", "sample_pdf", "dir", "pdf", "eval"):
         a, b = np.atleast_2d(g[f].T).T.astype(np.float64), np.atleast_2d(o[f].T).T.astype(np.float64)
         finite = np.isfinite(a) & np.isfinite(b)
         assert (np.isfinite(a) == np.isfinite(b)).all(), f
-        err = np.abs(a - b)[finite] / np.maximum(np.abs(b)[finite], 1e-3)
-        frac_bad = float((err > 1e-4).mean()) if err.size else 0.0
+        err = np.where(finite, np.abs(a - b) / np.maximum(np.abs(b), 1e-3), 0.0)
+        frac_bad = float((err[finite] > 1e-4).mean()) if finite.any() else 0.0
+        # the budget is for libm's last ulp at a branch (a Fresnel / total-internal-reflection threshold flips and the record
+        # takes the other lobe): every offender is printed with its material so that a real regression cannot hide in it
+        rows = np.nonzero((err > 1e-4).any(axis=1))[0]
+        if len(rows):
+            w = rows[np.argmax(err[rows].max(axis=1))]
+            kinds = sorted({int(mat_type[r]) for r in rows}) if mat_type is not None else "?"
+            print(f"{key} {f}: {len(rows)} / {len(err)} records beyond 1e-4 ({frac_bad:.3%} of entries), material types {kinds}; worst: record {w} "
+                  f"(material node {int(recs['mat_node'][w])}, rnd {recs['rnd'][w]}, in {recs['in_dir'][w]}): gpu {a[w]} oracle {b[w]}")
         assert frac_bad <= 2e-3, f"{f}: {frac_bad:.4%} of table entries beyond 1e-4"
     cu.close()
 

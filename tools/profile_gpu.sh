@@ -12,10 +12,10 @@ export POLARIS_SCENE_CACHE=${POLARIS_SCENE_CACHE:-/tmp/polaris_scenes}
 CMD="python bench.py --config $C --steps 1 --warmup 1 --spp $SPP --no-cpu --chains 1"
 # every launch with its device time (cold-cache, serialised: compare shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}_${C}.csv $CMD > gpurun_out/launches_${R}_${C}.out 2>&1
-# two launches per class, the first two bounces of the THIRD sample (warm caches, and the launches that hold the most rays:
-# k_trace: 4 launches per sample, k_shade: 5, k_primary: 1)
-for KS in k_trace:8 k_shade:10 k_primary:2; do
-  K=${KS%%:*}; SKIP=${KS##*:}
-  ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 2 -f -o gpurun_out/prof_${K}_${R}_${C} $CMD > gpurun_out/prof_${K}_${R}_${C}.out 2>&1
+# every launch of a class in ONE batch of samples, the third batch of the run (warm caches): k_trace has 4 launches per batch,
+# k_shade 5, k_primary 1 (2 captured) -- the per-launch means then describe the same launches bench.py's roofline pass times
+for KS in k_trace:8:4 k_shade:10:5 k_primary:2:2; do
+  K=${KS%%:*}; REST=${KS#*:}; SKIP=${REST%%:*}; CNT=${REST##*:}
+  ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c $CNT -f -o gpurun_out/prof_${K}_${R}_${C} $CMD > gpurun_out/prof_${K}_${R}_${C}.out 2>&1
 done
 ls -la gpurun_out | grep "${R}_${C}"

@@ -25,8 +25,8 @@ def raw(rep):
     return rows[0], rows[1], rows[2:]
 
 
-md = [f"# ncu summary {R} (bench.py --config {CFG} --steps 1 --warmup 1 --spp 4 --chains 1, one B200)\n",
-      "`--set full --clock-control none --import-source on`, two launches per kernel class (skip 6).  Durations under ncu are",
+md = [f"# ncu summary {R} (bench.py --config {CFG} --steps 1 --warmup 1 --spp 8 --chains 1, one B200)\n",
+      "`--set full --clock-control none --import-source on`, every launch of the class in one batch of samples (the third of the run).  Durations under ncu are",
       "cold-cache and serialised: compare shares, not absolutes.  dram bytes are per launch.\n"]
 traffic = {}
 for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
@@ -35,13 +35,13 @@ for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
         continue
     hdr, units, rows = raw(rep)
     md.append(f"## {k}\n")
-    md.append("| metric | unit | launch 1 | launch 2 |")
-    md.append("|---|---|---|---|")
+    md.append("| metric | unit | " + " | ".join(f"launch {k + 1}" for k in range(len(rows))) + " |")
+    md.append("|---|---|" + "---|" * len(rows))
     vals = []
     for key in KEYS:
         if key in hdr:
             i = hdr.index(key)
-            md.append(f"| {key} | {units[i]} | " + " | ".join(r[i] for r in rows[:2]) + " |")
+            md.append(f"| {key} | {units[i]} | " + " | ".join(r[i] for r in rows) + " |")
     stall = collections.OrderedDict()
     for i, h in enumerate(hdr):
         if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
@@ -55,7 +55,7 @@ for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
-        tb = [float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1) for r in rows[:2]]
+        tb = [float(r[ir]) * scale.get(units[ir], 1) + float(r[iw]) * scale.get(units[iw], 1) for r in rows]
         def col(name, row=0, default=None):
             try:
                 return float(rows[row][hdr.index(name)])
@@ -64,14 +64,24 @@ for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
         ent = {"dram_bytes": sum(tb) / len(tb)}
         try:
             il0 = hdr.index("lts__t_sectors.sum")
-            ent["l2_bytes"] = sum(float(r[il0]) * 32.0 for r in rows[:2]) / len(rows[:2])
+            ent["l2_bytes"] = sum(float(r[il0]) * 32.0 for r in rows) / len(rows)
         except Exception:
             pass
-        ent["lanes_active"] = col("smsp__thread_inst_executed_per_inst_executed.ratio")
-        ent["ipc"] = col("sm__inst_executed.avg.per_cycle_elapsed")
-        ent["l1_hit_pct"] = col("l1tex__t_sector_hit_rate.pct")
-        ent["l2_hit_pct"] = col("lts__t_sector_hit_rate.pct")
-        ent["dram_pct_of_peak_under_ncu"] = col("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
+        ent["launches_captured"] = len(rows)
+        # instruction-weighted over the captured launches (the first bounce's launch dominates)
+        def wmean(name):
+            try:
+                wi = hdr.index("smsp__inst_executed.sum")
+                w = [float(r[wi]) for r in rows]
+                v = [float(r[hdr.index(name)]) for r in rows]
+                return sum(a * b for a, b in zip(v, w)) / max(1.0, sum(w))
+            except Exception:
+                return col(name)
+        ent["lanes_active"] = wmean("smsp__thread_inst_executed_per_inst_executed.ratio")
+        ent["ipc"] = wmean("sm__inst_executed.avg.per_cycle_elapsed")
+        ent["l1_hit_pct"] = wmean("l1tex__t_sector_hit_rate.pct")
+        ent["l2_hit_pct"] = wmean("lts__t_sector_hit_rate.pct")
+        ent["dram_pct_of_peak_under_ncu"] = wmean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
         ent["registers"] = col("launch__registers_per_thread")
         top = sorted(stall.items(), key=lambda kv: -kv[1])[:2]
         ent["top_stalls"] = {h: round(v / tot, 3) for h, v in top}
@@ -80,10 +90,10 @@ for k in ("k_shade", "k_trace", "k_query", "k_occlusion", "k_primary"):
         traffic[k] = ent
         # derived: achieved HBM and L2 GB/s under the profiler (cold caches, serialised launches)
         it, il = hdr.index("gpu__time_duration.sum"), hdr.index("lts__t_sectors.sum")
-        secs = [float(r[it]) * tscale.get(units[it], 1e-9) for r in rows[:2]]
-        l2 = [float(r[il]) * 32.0 for r in rows[:2]]  # 32-byte sectors
+        secs = [float(r[it]) * tscale.get(units[it], 1e-9) for r in rows]
+        l2 = [float(r[il]) * 32.0 for r in rows]  # 32-byte sectors
         md.append("derived: HBM " + " / ".join(f"{b / t / 1e9:.0f}" for b, t in zip(tb, secs)) + " GB/s, L2 "
-                  + " / ".join(f"{b / t / 1e9:.0f}" for b, t in zip(l2, secs)) + " GB/s (launch 1 / launch 2)\n")
+                  + " / ".join(f"{b / t / 1e9:.0f}" for b, t in zip(l2, secs)) + " GB/s (per launch, under the profiler)\n")
     except Exception:
         pass
 os.makedirs(P, exist_ok=True)
@@ -107,7 +117,7 @@ if traffic:
     except Exception:
         allt = {}
     allt = {k: v for k, v in allt.items() if isinstance(v, dict)}  # drop the round-1 flat layout
-    traffic["_note"] = f"per launch, ncu --set full --clock-control none, {R}, bench.py --config {CFG} --spp 4 --chains 1 (mean of 2 launches)"
+    traffic["_note"] = f"per launch, ncu --set full --clock-control none, {R}, bench.py --config {CFG} --spp 8 --chains 1 (mean over every launch of the class in one batch of samples)"
     allt[CFG] = traffic
     json.dump(allt, open(tp, "w"), indent=1)
 print("\n".join(md[:12]))
