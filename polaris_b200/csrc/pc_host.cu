@@ -789,35 +789,47 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
     const size_t nMat = v->material_nodes_bytes / 64;
     if (v->scene_diffuse_mat_index < -1 || v->scene_diffuse_mat_index >= (int64_t)nMat)
         return fail(tr, PC_ERR_BAD_SCENE, "scene diffuse material index %d out of range (-1 = none, %zu material nodes)", v->scene_diffuse_mat_index, nMat);
+    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
+    // The copies of the ten flat buffers start first: from page-locked host memory (pc_host_register) they run while this
+    // thread derives the traversal layout and validates the scene below.  A scene that fails validation leaves the handle
+    // without scene data (its buffers were overwritten).
+    // The per-sample graph survives a re-upload when every device buffer keeps its address and the scene scalars are
+    // unchanged (DevBuf::alloc reuses allocations of the same size; GraphKey compares the DScene by value): an e2e loop that
+    // re-sends the same scene every frame does not re-instantiate the kernel nodes each time
+    tr->hasScene = false;
+    if ((rc = upload(tr, tr->verts, v->vertices, v->vertices_bytes))) return rc;
+    if ((rc = upload(tr, tr->normals, v->normals, v->normals_bytes))) return rc;
+    if ((rc = upload(tr, tr->uvs, v->uvs, v->uvs_bytes))) return rc;
+    if ((rc = upload(tr, tr->texData, v->texture_data, v->texture_data_bytes))) return rc;
+    if ((rc = upload(tr, tr->matIdx, v->material_indices, v->material_indices_bytes))) return rc;
+    if ((rc = upload(tr, tr->bvh, v->bvh_nodes, v->bvh_nodes_bytes))) return rc;
+    if ((rc = upload(tr, tr->inst, v->mesh_instances, v->mesh_instances_bytes))) return rc;
+    if ((rc = upload(tr, tr->mats, v->material_nodes, v->material_nodes_bytes))) return rc;
+    if ((rc = upload(tr, tr->texMeta, v->texture_metadata, v->texture_metadata_bytes))) return rc;
+    if ((rc = upload(tr, tr->emissives, v->emissives, v->emissives_bytes))) return rc;
     pc_layout::Builder lb((const pc_layout::RefNode *)v->bvh_nodes, v->bvh_nodes_bytes / 32,
                           (const pc_layout::RefInstance *)v->mesh_instances, v->mesh_instances_bytes / 80,
                           (const pc_layout::Q *)v->vertices, v->vertices_bytes / 16, /*derive_tris=*/false);
     pc_layout::Layout L = lb.build();
-    if (!L.error.empty()) return fail(tr, PC_ERR_BAD_SCENE, "%s", L.error.c_str());
+    auto bad_scene = [&](int code, const std::string &msg) {
+        cudaStreamSynchronize(tr->stream);  // the caller's buffers are no longer read when this returns
+        return fail(tr, code, "%s", msg.c_str());
+    };
+    if (!L.error.empty()) return bad_scene(PC_ERR_BAD_SCENE, L.error);
 #ifdef PC_WIDE_BVH
     pc_layout::Builder::build_wide(L);
 #endif
     if (L.stack_need > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
-        return fail(tr, PC_ERR_STACK_DEPTH, "BVH needs a %d-entry traversal stack, the kernels have %d", L.stack_need, PC_STACK_SIZE);
+        return bad_scene(PC_ERR_STACK_DEPTH, "BVH needs a " + std::to_string(L.stack_need) + "-entry traversal stack, the kernels have " + std::to_string(PC_STACK_SIZE));
     {   // validate what the shading kernels index with
         const uint32_t *mi = (const uint32_t *)v->material_indices;
-        for (size_t i = 0; i < v->material_indices_bytes / 4; i++)
-            if (mi[i] >= nMat) return fail(tr, PC_ERR_BAD_SCENE, "triangle %zu references material node %u of %zu", i, mi[i], nMat);
+        const size_t nTri = v->material_indices_bytes / 4;
+        size_t badAt = nTri;
+        for (size_t i = 0; i < nTri; i++)
+            if (mi[i] >= nMat) { badAt = i; break; }
+        if (badAt < nTri)
+            return bad_scene(PC_ERR_BAD_SCENE, "triangle " + std::to_string(badAt) + " references material node " + std::to_string(mi[badAt]) + " of " + std::to_string(nMat));
     }
-    CU(tr, PC_ERR_KERNEL, cudaStreamSynchronize(tr->stream));
-    // the per-sample graph survives a re-upload when every device buffer keeps its address and the scene scalars are
-    // unchanged (DevBuf::alloc reuses allocations of the same size; GraphKey compares the DScene by value): an e2e loop that
-    // re-sends the same scene every frame does not re-instantiate 48 kernel nodes per chain each time
-    if ((rc = upload(tr, tr->bvh, v->bvh_nodes, v->bvh_nodes_bytes))) return rc;
-    if ((rc = upload(tr, tr->inst, v->mesh_instances, v->mesh_instances_bytes))) return rc;
-    if ((rc = upload(tr, tr->mats, v->material_nodes, v->material_nodes_bytes))) return rc;
-    if ((rc = upload(tr, tr->texData, v->texture_data, v->texture_data_bytes))) return rc;
-    if ((rc = upload(tr, tr->texMeta, v->texture_metadata, v->texture_metadata_bytes))) return rc;
-    if ((rc = upload(tr, tr->verts, v->vertices, v->vertices_bytes))) return rc;
-    if ((rc = upload(tr, tr->normals, v->normals, v->normals_bytes))) return rc;
-    if ((rc = upload(tr, tr->uvs, v->uvs, v->uvs_bytes))) return rc;
-    if ((rc = upload(tr, tr->matIdx, v->material_indices, v->material_indices_bytes))) return rc;
-    if ((rc = upload(tr, tr->emissives, v->emissives, v->emissives_bytes))) return rc;
     if ((rc = upload(tr, tr->node64, L.node64.data(), L.node64.size() * 16))) return rc;
 #ifdef PC_WIDE_BVH
     if ((rc = upload(tr, tr->node128, L.node128.data(), L.node128.size() * 16))) return rc;

@@ -378,6 +378,24 @@ def test_error_behaviour():
         tr.merge_output(C.oracle_for(sc, 64, 64), T.make_block_request(64, 64))
     with pytest.raises(T.ErrUnsupportedChangeType):
         tr.update_state(T.SYNCHRONOUS, 17, None)
+    # a scene that fails validation is refused and leaves the handle without scene data; a good one recovers it
+    import copy
+    bad = copy.deepcopy(sc)
+    bad.material_index = bad.material_index.copy()
+    bad.material_index[3] = len(bad.material_nodes) + 7
+    with pytest.raises(T.TracerError) as ei:
+        tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, bad)
+    assert ei.value.code == _lib.ERR_BAD_SCENE and "triangle 3" in str(ei.value)
+    bad2 = copy.deepcopy(sc)
+    bad2.scene_diffuse_mat_index = -2
+    with pytest.raises(T.TracerError):
+        tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, bad2)
+    tr._change_buffer = {}  # (like the reference, a failed commit keeps its change buffered: tracer.go:161-191)
+    tr._has_scene = True    # the binding's own guard out of the way: the library must refuse by itself
+    with pytest.raises(T.ErrNoSceneData):
+        tr.trace(T.make_block_request(64, 64, num_bounces=1), T.splitmix_seeds(1, 2))
+    tr.update_state(T.SYNCHRONOUS, T.SCENE_DATA, sc)
+    tr.trace(T.make_block_request(64, 64, num_bounces=1), T.splitmix_seeds(1, 2))
     tr.close()
 
 
