@@ -378,6 +378,7 @@ def test_error_behaviour():
         tr.merge_output(C.oracle_for(sc, 64, 64), T.make_block_request(64, 64))
     with pytest.raises(T.ErrUnsupportedChangeType):
         tr.update_state(T.SYNCHRONOUS, 17, None)
+    tr._change_buffer = {}  # (like the reference, a failed commit keeps its change buffered: tracer.go:161-191)
     # a scene that fails validation is refused and leaves the handle without scene data; a good one recovers it
     import copy
     bad = copy.deepcopy(sc)
