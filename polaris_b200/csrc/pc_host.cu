@@ -649,6 +649,30 @@ int pc_create(int ordinal, const char *id, pc_tracer **out) {
         delete tr;
         return PC_ERR_NO_DEVICE;
     }
+    // Shared-memory carve-out of the traversal kernels: just enough for the resident blocks' stacks, the rest of the SM's
+    // 256 KB stays L1 (the scene is re-read by every ray).  Left to the driver the carve-out came out larger: asking for the
+    // minimum measured +1.5 % on configs 2 and 3, +0.5 % on config 4 (profiles/ab_r02j.txt; 72 % like k_shade: k_trace 728 -> 763 us;
+    // a 5-entry shared stack under a 32 KB carve-out: +0.6 / -0.5 / +0.1 %, ab_r02k.txt).  PC_TRAV_CARVEOUT (percent)
+    // overrides, -1 keeps the driver's choice.
+    {
+        auto carve = [&](auto kernel, int minBlocks) {
+#if defined(PC_TRAV_CARVEOUT)
+            const int pct = PC_TRAV_CARVEOUT;
+#else
+            cudaFuncAttributes fa{};
+            if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) { cudaGetLastError(); return; }
+            const size_t want = (size_t)minBlocks * (fa.sharedSizeBytes + 1024);
+            int pct = (int)((want * 100 + tr->prop.sharedMemPerMultiprocessor - 1) / tr->prop.sharedMemPerMultiprocessor);
+            if (pct > 100) pct = 100;
+#endif
+            if (pct >= 0 && cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct) != cudaSuccess) cudaGetLastError();
+        };
+        carve(k_primary<0, false>, PC_PRIMARY_MIN_BLOCKS); carve(k_primary<0, true>, PC_PRIMARY_MIN_BLOCKS);
+        carve(k_trace<false, false>, PC_TRAV_MIN_BLOCKS);  carve(k_trace<false, true>, PC_TRAV_MIN_BLOCKS);
+        carve(k_trace<true, false>, PC_TRAV_MIN_BLOCKS);   carve(k_trace<true, true>, PC_TRAV_MIN_BLOCKS);
+        carve(k_occlusion<false, false>, PC_OCC_MIN_BLOCKS); carve(k_occlusion<false, true>, PC_OCC_MIN_BLOCKS);
+        carve(k_query<false, false>, PC_TRAV_MIN_BLOCKS);  carve(k_query<false, true>, PC_TRAV_MIN_BLOCKS);
+    }
     // persistent grid: every SM full of traversal blocks (multiple of the SM count)
     int perSM = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_query<false, false>, TRAV_BLOCK, 0);

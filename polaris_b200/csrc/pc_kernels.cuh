@@ -260,7 +260,7 @@ __device__ __forceinline__ void trace_queue_units(const DScene &sc, Stack stack,
         if (unit >= n) break;
         const uint32_t j = unit + lane_id();
         if (lane_id() < size && j < n) {
-            const uint32_t i = perm ? __ldcs(perm + j) : j;  // which ray a lane walks changes nothing: results go to slot i
+            const uint32_t i = perm ? __ldcs(perm + j) : src.map(j);  // which ray a lane walks changes nothing: results go to slot i
             float3 o, d;
             float tmax;
             src.load(i, o, d, tmax);
@@ -303,7 +303,7 @@ __device__ __forceinline__ void trace_queue_refill(const DScene &sc, Stack stack
                 const uint32_t take = min(want - assigned, poolEnd - poolNext);
                 if (!busy && myRank >= assigned && myRank < assigned + take) {
                     const uint32_t j = poolNext + (myRank - assigned);
-                    const uint32_t i = perm ? __ldcs(perm + j) : j;
+                    const uint32_t i = perm ? __ldcs(perm + j) : src.map(j);
                     float3 o, d;
                     float tmax;
                     src.load(i, o, d, tmax);
@@ -354,6 +354,7 @@ __device__ __forceinline__ void trace_queue(const DScene &sc, Stack stack, uint3
 
 struct RaySource {  // rays[i] as stored by k_primary / k_shade
     const Ray *rays;
+    __device__ __forceinline__ uint32_t map(uint32_t j) const { return j; }
     __device__ __forceinline__ void load(uint32_t i, float3 &o, float3 &d, float &tmax) const {
         const Ray r = ld_ray(rays + i);
         o = xyz(r.origin); d = xyz(r.dir); tmax = r.origin.w;
@@ -480,12 +481,37 @@ __device__ __forceinline__ int traverse_packet(const DScene &sc, uint2 *stack, b
 }
 
 // generatePrimaryRays (camera.cl:5-58) as a ray source: ray i is pixel (i % frameW, i / frameW) of the block
+// PC_PRIMARY_TILES (default on): the j-th item of the work queue is not ray j but the ray of an 8 x 4 PIXEL TILE, so that the
+// 32 lanes of a warp walk a compact bundle instead of a 32 x 1 strip of the image (fewer instance / leaf boundaries inside
+// a warp).  A bijection on every sample slot's index range: rows [0, blockH & ~3) are tiled when frameW % 8 == 0, the ragged
+// rest keeps the linear order.  Nothing else changes -- ray i, its path record and its hit record live at slot i either way.
+// MEASURED (profiles/ab_r02j.txt): k_primary 4 391 -> 3 788 us on config 3, 1 800 -> 1 585 us on config 4, 456 -> 437 us on
+// config 2 (frames +2.3 / +2.5 / +0.1 %).  Making 2 x 2 groups of tiles consecutive in the queue adds nothing (ab_r02k.txt).
+#ifndef PC_PRIMARY_TILES
+#define PC_PRIMARY_TILES 1
+#endif
 struct PrimarySource {
     FrameBufs fb;
     CameraParams cam;
     uint32_t frameW, blockY, slotPaths;
     const uint32_t *seeds;      // camera seed of slot s at seeds[(curSample + s * slotStride) * seedsPerSample]
     uint32_t curSample, slotStride, seedsPerSample;
+    uint32_t tiledRays;         // how many of a slot's rays are tiled (see tiledCount): whole tiles only, the ragged rest stays linear
+    static __device__ __forceinline__ uint32_t tiledCount(uint32_t frameW, uint32_t blockH) {
+        return (frameW & 7u) == 0u ? frameW * (blockH & ~3u) : 0u;
+    }
+    __device__ __forceinline__ uint32_t map(uint32_t j) const {
+#if PC_PRIMARY_TILES
+        const uint32_t slot = j / slotPaths, local = j - slot * slotPaths;
+        if (local >= tiledRays) return j;
+        const uint32_t l = local & 31u;
+        const uint32_t tile = local >> 5, tilesX = frameW >> 3;
+        const uint32_t ty = tile / tilesX, tx = tile - ty * tilesX;
+        return slot * slotPaths + (ty * 4u + (l >> 3)) * frameW + tx * 8u + (l & 7u);
+#else
+        return j;
+#endif
+    }
     __device__ __forceinline__ void load(uint32_t index, float3 &o, float3 &d, float &tmax) const {
         const uint32_t slot = index / slotPaths, local = index - slot * slotPaths;  // ray index == slot * slotPaths + path index
         const uint32_t gx = local % frameW, gy = local / frameW;
@@ -570,7 +596,8 @@ __global__ void __launch_bounds__(TRAV_BLOCK, PC_PRIMARY_MIN_BLOCKS) k_primary(D
     uint32_t missed = 0;
     if (MODE == 0) {
         PC_TRAV_STACK(stack);
-        PrimarySource src{fb, cam, frameW, blockY, n, seeds, curSample, slotStride, seedsPerSample};
+        PrimarySource src{fb, cam, frameW, blockY, n, seeds, curSample, slotStride, seedsPerSample,
+                          PrimarySource::tiledCount(frameW, blockH)};
         HitSink<COUNT> sink{fb.hitFlags, fb.hits, 0u};
         trace_queue<false, COUNT>(sc, stack, &ctl->queueHead[queueSlot], total, st, src, sink);
         missed = sink.missed;
