@@ -752,6 +752,19 @@ __device__ __forceinline__ uint32_t stackPop(SmemStack<DEPTH, STRIDE> s, int &sp
 }
 #endif
 
+// PC_POP_CULL: a closest-hit walk pushes the far child's ENTRY DISTANCE next to its reference (two stack words per entry) and
+// tests it again when the entry is popped: by then the near subtree has usually produced a closer hit, and without the test
+// a popped leaf reference goes straight to its (up to 10) triangle tests and a popped inner node costs a fetch and two slab
+// tests before its children are culled.  Same predicate as at push time (entry > best * PC_CULL_SLACK), so the hit record is
+// unchanged: a culled subtree cannot hold a hit with t <= best.  Instance markers carry distance 0 and are never culled.
+// Any-hit walks have no "best so far" and keep one-word entries.
+// MEASURED AND REJECTED (round 2, profiles/ab_r02l.txt): with nearest-first order and culling at push time there is little
+// left to cull at pop time -- on real bounce rays (host build of this header) 1 % fewer node / triangle steps on config 2,
+// 8 % on config 3, 2 % on config 4, hit records identical -- and the second stack word plus the pop loop cost more:
+// k_trace 3 681 -> 3 885 us on config 3, 1 017 -> 1 064 us on config 4, unchanged on config 2.  Compiled out.
+#ifndef PC_POP_CULL
+#define PC_POP_CULL 0
+#endif
 // Stack-based traversal of the derived layout, written as a per-ray state machine so that the same
 // three steps serve the plain loop below (host build / tests) and the persistent kernels, which
 // interleave them with warp-level refilling of finished lanes (pc_kernels.cuh).
@@ -782,6 +795,30 @@ PC_HD void travInit(Trav &t, const DScene &sc, float3 o0, float3 d0, float tmaxR
     t.sp = 0;
 }
 
+template <bool ANY_HIT, class Stack>
+PC_HD void travPush(Trav &t, Stack stack, uint32_t ref, float entry) {
+    stackPush(stack, t.sp, ref);
+#if PC_POP_CULL
+    if (!ANY_HIT) stackPush(stack, t.sp, f2u(entry));
+#endif
+}
+// next reference to visit, REF_DONE when the stack is exhausted
+template <bool ANY_HIT, class Stack>
+PC_HD uint32_t travPop(Trav &t, Stack stack) {
+#if PC_POP_CULL
+    if (!ANY_HIT) {
+        const float lim = t.best.wuvt.w * PC_CULL_SLACK;
+        while (t.sp) {
+            const float entry = u2f(stackPop(stack, t.sp));
+            const uint32_t ref = stackPop(stack, t.sp);
+            if (!(entry > lim)) return ref;
+        }
+        return REF_DONE;
+    }
+#endif
+    return t.sp ? stackPop(stack, t.sp) : REF_DONE;
+}
+
 // Reference classes: inner node (bit 31 clear), triangle leaf (bits 31:30 == 10), and the "other"
 // leaf-type references with bits 31:30 == 11 (instance entry, the exit marker, REF_DONE).
 PC_HD bool refIsTriLeaf(uint32_t c) { return (c >> 30) == 2u; }
@@ -805,7 +842,7 @@ PC_HD void travInner(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (wl && wr) {
         bool leftFirst = tl <= tr;
         const uint32_t farRef = leftFirst ? rref : lref;
-        stackPush(stack, t.sp, farRef);
+        travPush<ANY_HIT>(t, stack, farRef, leftFirst ? tr : tl);
         t.cur = leftFirst ? lref : rref;
 #if defined(__CUDA_ARCH__) && defined(PC_PREFETCH_FAR)
         // the far child is fetched when it is popped, many steps later: ask for its record now (experiment)
@@ -815,7 +852,7 @@ PC_HD void travInner(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     } else if (wl || wr) {
         t.cur = wl ? lref : rref;
     } else {
-        t.cur = t.sp ? stackPop(stack, t.sp) : REF_DONE;
+        t.cur = travPop<ANY_HIT>(t, stack);
     }
 }
 
@@ -856,19 +893,19 @@ PC_HD void travInnerWide(Trav &t, const DScene &sc, Stack stack, TravStats &st) 
     wideSwap(e1, r1, e3, r3);
     wideSwap(e1, r1, e2, r2);  // e0 <= e1 <= e2 <= e3, rejected children (FLT_MAX) last
     if (e0 == FLT_MAX) {
-        t.cur = t.sp ? stackPop(stack, t.sp) : REF_DONE;
+        t.cur = travPop<ANY_HIT>(t, stack);
         return;
     }
-    if (e3 < FLT_MAX) stackPush(stack, t.sp, r3);
-    if (e2 < FLT_MAX) stackPush(stack, t.sp, r2);
-    if (e1 < FLT_MAX) stackPush(stack, t.sp, r1);
+    if (e3 < FLT_MAX) travPush<ANY_HIT>(t, stack, r3, e3);
+    if (e2 < FLT_MAX) travPush<ANY_HIT>(t, stack, r2, e2);
+    if (e1 < FLT_MAX) travPush<ANY_HIT>(t, stack, r1, e1);
     t.cur = r0;
 }
 #endif
 
 // Instance entry (:237-249) or the exit marker that restores the world-space ray (:330-335).
 // Returns 0 to continue, 1 when the walk is over.  Requires bits 31:30 == 11 and cur != REF_DONE.
-template <bool COUNT, class Stack>
+template <bool ANY_HIT, bool COUNT, class Stack>
 PC_HD int travOther(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (t.cur == REF_POP_INSTANCE || t.cur == REF_POP_TRANSLATED) {
         t.o = t.o0;
@@ -876,9 +913,8 @@ PC_HD int travOther(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
             t.d = t.d0;
             t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
         }
-        if (t.sp == 0) return 1;
-        t.cur = stackPop(stack, t.sp);
-        return 0;
+        t.cur = travPop<ANY_HIT>(t, stack);
+        return t.cur == REF_DONE ? 1 : 0;
     }
     if (COUNT) st.instances++;
     t.curInst = t.cur & 0x3FFFFFFFu;
@@ -892,14 +928,14 @@ PC_HD int travOther(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
         // reciprocals on the way in or out
         float4 m3 = PC_LDG(ip + 4);
         t.o = f3(t.o.x + m3.x, t.o.y + m3.y, t.o.z + m3.z);
-        stackPush(stack, t.sp, REF_POP_TRANSLATED);
+        travPush<ANY_HIT>(t, stack, REF_POP_TRANSLATED, 0.0f);
     } else if (!(iflags & INST_FLAG_IDENTITY)) {
         // identity matrices are skipped: x*1 + y*0 + z*0 + 0 == x exactly for finite inputs
         float4 m0 = PC_LDG(ip + 1), m1 = PC_LDG(ip + 2), m2 = PC_LDG(ip + 3), m3 = PC_LDG(ip + 4);
         t.o = mul4x1(t.o, m0, m1, m2, m3);
         t.d = mul3x1(t.d, m0, m1, m2);
         t.invDir = f3(1.0f / t.d.x, 1.0f / t.d.y, 1.0f / t.d.z);
-        stackPush(stack, t.sp, REF_POP_INSTANCE);
+        travPush<ANY_HIT>(t, stack, REF_POP_INSTANCE, 0.0f);
     }
     t.cur = f2u(hdr.x);
     return 0;
@@ -939,9 +975,8 @@ PC_HD int travTris(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
         tp += 3;
         a = PC_LDG(tp);
     }
-    if (t.sp == 0) return 1;
-    t.cur = stackPop(stack, t.sp);
-    return 0;
+    t.cur = travPop<ANY_HIT>(t, stack);
+    return t.cur == REF_DONE ? 1 : 0;
 }
 
 // Any leaf-type reference.  Requires t.cur & REF_LEAF.
@@ -949,7 +984,7 @@ template <bool ANY_HIT, bool COUNT, class Stack>
 PC_HD int travLeaf(Trav &t, const DScene &sc, Stack stack, TravStats &st) {
     if (t.cur == REF_DONE) return 1;
     if (refIsTriLeaf(t.cur)) return travTris<ANY_HIT, COUNT>(t, sc, stack, st);
-    return travOther<COUNT>(t, sc, stack, st);
+    return travOther<ANY_HIT, COUNT>(t, sc, stack, st);
 }
 
 // The plain loop: inner-node steps and leaf work in separate loops ("while-while"), so a warp

@@ -843,8 +843,9 @@ int pc_upload_scene(pc_tracer *tr, const pc_scene_view *v) {
 #ifdef PC_WIDE_BVH
     pc_layout::Builder::build_wide(L);
 #endif
-    if (L.stack_need > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
-        return bad_scene(PC_ERR_STACK_DEPTH, "BVH needs a " + std::to_string(L.stack_need) + "-entry traversal stack, the kernels have " + std::to_string(PC_STACK_SIZE));
+    const int stackWords = PC_POP_CULL ? 2 : 1;  // closest-hit entries carry their entry distance under PC_POP_CULL
+    if (L.stack_need * stackWords > PC_STACK_SIZE)  // the reference reserves 32 entries and never checks
+        return bad_scene(PC_ERR_STACK_DEPTH, "BVH needs a " + std::to_string(L.stack_need) + "-entry traversal stack, the kernels have " + std::to_string(PC_STACK_SIZE / stackWords));
     {   // validate what the shading kernels index with
         const uint32_t *mi = (const uint32_t *)v->material_indices;
         const size_t nTri = v->material_indices_bytes / 4;

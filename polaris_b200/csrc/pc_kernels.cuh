@@ -326,7 +326,7 @@ __device__ __forceinline__ void trace_queue_refill(const DScene &sc, Stack stack
                 if (searching) {
                     if (!(t.cur & REF_LEAF)) {
                         travInner<ANY_HIT, COUNT>(t, sc, stack, st);
-                    } else if (travOther<COUNT>(t, sc, stack, st)) {
+                    } else if (travOther<ANY_HIT, COUNT>(t, sc, stack, st)) {
                         t.cur = REF_DONE;
                     }
                 }
