@@ -12,6 +12,10 @@
 //            TextureMetadata (16), VertexList (16), NormalList (16), UvList (8), MaterialIndex (4), EmissivePrimitives (80)
 //            -- the upload order of tracer/opencl/buffers.go:180-191
 //   trailer  int32 SceneDiffuseMatIndex, int32 SceneEmissiveMatIndex, Camera.Position, LookAt, Up (3 x float32 each), float32 FOV
+//
+// Dump BEFORE the first Camera.Update() (i.e. before cmd/render.go's SetupProjection): Update stores Position + the
+// normalised direction back into LookAt (camera.go:99-108), and a reader that normalises that again is one ulp off the
+// frustum the renderer derived.  The Python writer keeps the constructed LookAt for the same reason.
 package scene
 
 import (

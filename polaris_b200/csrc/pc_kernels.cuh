@@ -837,8 +837,23 @@ __device__ __forceinline__ void lookback(volatile unsigned long long *status, ui
 //      written out -- the output order is parent ray order, whichever lane did the arithmetic for a ray.
 // ------------------------------------------------------------------------------------------------
 constexpr int SHADE_WARPS = SHADE_BLOCK / 32;
-constexpr int SHADE_KEYS = 64;  // histogram bins: material roots modulo 62, misses, inactive lanes
-constexpr uint32_t KEY_MISS = SHADE_KEYS - 2, KEY_INACTIVE = SHADE_KEYS - 1;
+constexpr int SHADE_KEYS = 64;  // histogram bins: material roots modulo 61, roulette victims, misses, inactive lanes
+constexpr uint32_t KEY_KILLED = SHADE_KEYS - 3, KEY_MISS = SHADE_KEYS - 2, KEY_INACTIVE = SHADE_KEYS - 1;
+// PC_SORT_RR (default on): from the bounce where Russian roulette starts, a ray that the roulette is going to kill gets a sort
+// key of its own.  The decision (pt_integrator.cl:113-124) depends on the path's throughput and on the third draw of the
+// ray's random stream only -- not on the surface -- so the sort phase can foresee it; shadeHit still makes the decision
+// itself, the key is a scheduling hint and cannot change a result.  Without it half of the lanes of every chunk return
+// at the roulette and the BxDF / light-sampling code that follows -- most of shadeHit -- runs half empty (ncu, config 2:
+// 11.7 of 32 lanes in the launch of bounce 3 against 24-27 before the roulette starts).
+#ifndef PC_SORT_RR
+#define PC_SORT_RR 1
+#endif
+// PC_SORT_LEAF: key a hit by the LEAF of its material tree instead of the root, as far as the leaf can be foreseen in the sort
+// phase (constant mixes draw from the ray's own random stream; texture-weighted mixes and disperse nodes end the forecast).
+// A layered material then no longer puts its diffuse, conductor and dielectric lanes into the same chunk.  Also only a hint.
+#ifndef PC_SORT_LEAF
+#define PC_SORT_LEAF 0
+#endif
 // Rays per thread and tile.  A tile is SHADE_BLOCK * SHADE_RPT consecutive rays; after the sort the CTA's
 // warps PULL 32-ray chunks of the sorted tile from a shared counter, so a warp that drew a cheap material
 // (diffuse) takes the next chunk instead of waiting at the tile's barrier for the warp that drew the
@@ -957,7 +972,43 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
                 k = KEY_MISS;
                 if (__ldcs(fb.hitFlags + i)) {
                     tri = __ldcs(&fb.hits[i].meta).y;
-                    k = PC_LDG(sc.matIndex + tri) % (uint32_t)(SHADE_KEYS - 2);
+                    uint32_t node = PC_LDG(sc.matIndex + tri);
+#if PC_SORT_RR || PC_SORT_LEAF
+                    const bool rr = PC_SORT_RR && bounce >= minBouncesForRR;  // uniform
+                    if (PC_SORT_LEAF || rr) {
+                        const uint32_t sslot = oneSlot ? 0u : slotOf(sh.baseA, i);
+                        uint2 rnd = make_uint2(sh.seed[sslot], i - sh.baseA[sslot]);  // shadeHit's stream (pt_integrator.cl:81-84)
+                        randomGetSample2f(rnd);
+                        randomGetSample2f(rnd);
+                        const float2 sample2 = randomGetSample2f(rnd);
+                        bool killed = false;
+                        if (rr) {
+                            const uint32_t pathIndex = (uint32_t)__ldcs(&fb.rays[a][i].dir.w);
+                            const float4 T = __ldcs(&fb.paths[(size_t)sslot * slotPaths + pathIndex].throughput);
+                            const float rrProbability = cl_max(cl_min(0.5f, 0.2126f * T.x + 0.7152f * T.y + 0.0722f * T.z), 0.01f);
+                            killed = rrProbability < sample2.x;
+                        }
+#if PC_SORT_LEAF
+                        // matSelectNode's walk (material_sampler.cl:21-88) as far as it can be foreseen without the surface: constant
+                        // mixes draw from the same stream, bump / normal maps do not draw; a mix map (texture weight) or a disperse
+                        // node (path flags) ends the forecast and keys the ray by that node
+                        for (int guard = 0; guard < 8 && !killed; guard++) {
+                            const float4 hdr = PC_LDG(sc.matNodes + 4 * (size_t)node);
+                            const uint32_t type = f2u(hdr.x);
+                            if (type == OP_MIX) {
+                                const float2 smp = randomGetSample2f(rnd);
+                                node = smp.x < PC_LDG(sc.matNodes + 4 * (size_t)node + 1).x ? f2u(hdr.y) : f2u(hdr.z);
+                            } else if (type == OP_BUMP_MAP || type == OP_NORMAL_MAP) {
+                                node = f2u(hdr.y);
+                            } else {
+                                break;
+                            }
+                        }
+#endif
+                        if (killed) node = 0xFFFFFFFFu;
+                    }
+#endif
+                    k = node == 0xFFFFFFFFu ? KEY_KILLED : node % (uint32_t)(SHADE_KEYS - 3);
                 }
             }
             sh.hitTri[slot] = tri;

@@ -53,6 +53,11 @@ class Camera:
     view_mat: np.ndarray = field(default_factory=gt.ident4)
     proj_mat: np.ndarray = field(default_factory=gt.ident4)
     frustrum: np.ndarray = field(default_factory=lambda: np.zeros((4, 4), dtype=F))
+    look_at_given: np.ndarray | None = None  # LookAt as constructed: Update() replaces look_at by position + unit direction
+
+    def __post_init__(self):
+        if self.look_at_given is None:
+            self.look_at_given = np.array(self.look_at, dtype=F)
 
     def setup_projection(self, aspect):
         self.proj_mat = gt.perspective4(self.fov, aspect, 1, 1000)
@@ -185,7 +190,9 @@ class Scene:
             f.write(struct.pack("<ii", self.scene_diffuse_mat_index, self.scene_emissive_mat_index))
             cam = self.camera
             f.write(np.asarray(cam.position, dtype=F).tobytes())
-            f.write(np.asarray(cam.look_at, dtype=F).tobytes())
+            # LookAt as it was BEFORE Update() (camera.go: Update stores Position + normalised direction back into LookAt, and
+            # normalising that again differs in the last ulp): a loaded scene then derives the very same frustum
+            f.write(np.asarray(cam.look_at_given, dtype=F).tobytes())
             f.write(np.asarray(cam.up, dtype=F).tobytes())
             f.write(struct.pack("<f", cam.fov))
 

@@ -2,6 +2,7 @@
 tests hold for this path -- BVH builder, scene compiler, block schedulers, material type
 codes, the fixture cube -- plus the properties the compiled buffers must have for the tracer ABI.
 """
+import os
 import numpy as np
 import pytest
 
@@ -206,16 +207,30 @@ def test_compiled_scene_invariants(key):
     assert np.abs(sc.vertices[:, :3]).max() <= 100.0
 
 
-def test_scene_dump_roundtrip(tmp_path):
-    sc = C.small_scene("c2", 64, 64)
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_scene_dump_roundtrip(tmp_path, key):
+    sc = C.small_scene(key, 64, 64)
     p = tmp_path / "scene.bin"
     sc.save(p)
     back = S.Scene.load(p)
     for name in S.Scene._SECTIONS:
         assert np.ascontiguousarray(getattr(sc, name)).tobytes() == np.ascontiguousarray(getattr(back, name)).tobytes(), name
     assert (back.scene_diffuse_mat_index, back.scene_emissive_mat_index) == (sc.scene_diffuse_mat_index, sc.scene_emissive_mat_index)
+    # the camera too, bit for bit: Update() writes position + unit direction back into LookAt (camera.go), so the dump keeps
+    # the LookAt the camera was constructed with (a c1 camera re-normalised from the updated LookAt is 1 ulp off)
     back.camera.setup_projection(F(1.0))
-    assert np.array_equal(back.camera.frustrum, sc.camera.frustrum)
+    assert back.camera.frustrum.tobytes() == sc.camera.frustrum.tobytes()
+
+
+def test_scene_cache_returns_the_same_scene(tmp_path, monkeypatch):
+    """POLARIS_SCENE_CACHE (scenes.build): the second build loads the dump and must be indistinguishable from the first."""
+    from polaris_b200 import scenes
+    from tests.golden.make_golden import scene_digest
+    monkeypatch.setenv("POLARIS_SCENE_CACHE", str(tmp_path))
+    a = scenes.build("c1_sphere", 96, 64)[0]
+    b = scenes.build("c1_sphere", 96, 64)[0]
+    assert os.path.exists(tmp_path / "c1_sphere_96x64.plrscn")
+    assert scene_digest(a) == scene_digest(b)
 
 
 def test_camera_frustum():
