@@ -915,6 +915,15 @@ int pc_set_camera(pc_tracer *tr, const float eye[3], const float frustum[16]) {
     return 0;
 }
 
+// Automatic sample slots: paths per launch aimed at.  8 M on small scenes; 16 M where walks are long (the scenes that also get
+// the refilling k_trace): measured +1.0 % on config 3 and +1.7 % on config 4, but -2 % on the 4K Cornell frame and +-0.4 % on
+// configs 1 and 2; 16 slots instead of 8 add nothing anywhere (profiles/ab_r02n.txt).
+#ifndef PC_SLOT_TARGET_PATHS
+#define PC_SLOT_TARGET_PATHS (8u << 20)
+#endif
+#ifndef PC_SLOT_TARGET_PATHS_LONG
+#define PC_SLOT_TARGET_PATHS_LONG (16u << 20)
+#endif
 // Tracer.Trace (tracer.go:194-247); dbg != nullptr: MonteCarloIntegrator(debugFlags) -- one chain, direct launches
 static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *seeds, size_t n_seeds, pc_stats *stats, DebugSink *dbg) {
     int rc = enter(tr);
@@ -962,9 +971,10 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
     if ((uint32_t)nc > spp) nc = spp ? (int)spp : 1;
     if (dbg) CU(tr, PC_ERR_ALLOC, tr->debugBuf.bytes >= (size_t)tr->W * tr->H * 4 + 16 ? cudaSuccess : tr->debugBuf.alloc((size_t)tr->W * tr->H * 4 + 16));
     // ---- sample slots: a set of launches carries `slots` samples of a chain (TraceCtl in pc_kernels.cuh): sample k of the
-    // request is traced by chain k % nc in slot (k / nc) % slots.  Automatic: enough slots for ~8 M paths per launch (profiles/ab_r02g.txt).
+    // request is traced by chain k % nc in slot (k / nc) % slots.  Automatic: enough slots for ~8 M paths per launch, 16 M on large scenes (profiles/ab_r02g.txt, ab_r02n.txt).
     const size_t blockRays = (size_t)req->frame_w * req->block_h;
-    int slots = tr->optSlots > 0 ? tr->optSlots : (int)((8u << 20) / (blockRays ? blockRays : 1));
+    const size_t slotTarget = tr->innerNodes >= PC_REFILL_AUTO_MIN_NODES ? (size_t)PC_SLOT_TARGET_PATHS_LONG : (size_t)PC_SLOT_TARGET_PATHS;
+    int slots = tr->optSlots > 0 ? tr->optSlots : (int)(slotTarget / (blockRays ? blockRays : 1));
     if (slots > MAX_SLOTS) slots = MAX_SLOTS;
     if (slots < 1 || dbg || tr->optPackets || tr->optRefOrder) slots = 1;
     if (slots > MAX_SLOTS) slots = MAX_SLOTS;
@@ -1054,6 +1064,7 @@ static int trace_common(pc_tracer *tr, pc_block_request *req, const uint32_t *se
         }
         // chains > 0 accumulated into their own buffers: add them in chain order, the block's rows only, one launch
         if (nc * slots > 1) {
+            static_assert(MAX_CHAINS * MAX_SLOTS <= MAX_CHAINS_X_SLOTS, "ChainAccs holds one pointer per (chain, slot)");
             ChainAccs ca;
             ca.n = 0;
             for (int c = 0; c < nc; c++)

@@ -65,7 +65,10 @@ enum StatIdx {
 // all a kernel needs is where each slot starts in each ray buffer (base[k][s]) to recover, for ray i of rays[k], its slot,
 // its slot-local index (the RNG key of pt_integrator.cl:81 -- results are bit-identical to tracing the samples one by
 // one), its path record (paths[slot * slotPaths + pathIndex]) and its accumulator (FrameBufs::slotAcc[slot]).
-constexpr int MAX_SLOTS = 8;
+#ifndef PC_MAX_SLOTS
+#define PC_MAX_SLOTS 8
+#endif
+constexpr int MAX_SLOTS = PC_MAX_SLOTS;
 constexpr int MAX_CHAINS_X_SLOTS = 64;
 struct TraceCtl {
     int numRays[3];            // [persist] the reference's three ray counters (buffers.go:69), over all slots
