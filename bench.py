@@ -349,6 +349,12 @@ def roofline_pass(tr, sc, w, h, block_y, block_h, prof_spp, seeds, config):
             measured["dram_frac"] = measured["dram_GBps"] / peak
         if prof.get("l2_bytes"):
             measured["l2_GBps"] = prof["l2_bytes"] / (avg_launch_us * 1e3)
+        if prof.get("ipc"):
+            # the roofline these kernels actually sit under: warp instructions issued per SM cycle of the 4 an SM can issue, and
+            # how many of a warp instruction's 32 lanes do useful work
+            measured["issue_slot_frac"] = prof["ipc"] / 4.0
+            if prof.get("lanes_active"):
+                measured["simd_frac"] = prof["lanes_active"] / 32.0
         measured["note"] = ("ncu --set full of this kernel class on this config (profiles/); bytes are per launch, rates use the "
                             "launch time measured HERE.  bound = what the counters show limits the kernel")
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -687,7 +687,10 @@ def test_ragged_frames_and_blocks():
     blocks, a sample count below the number of sample chains: every partially filled unit / tile path."""
     for (w, h), kw, opts in (((97, 61), dict(spp=3), {}), ((97, 61), dict(spp=3), {"primary_packets": 1}), ((33, 7), dict(spp=5, num_bounces=2), {}),
                              ((64, 64), dict(block_y=63, block_h=1, spp=2), {"fix_q4": 1}), ((130, 9), dict(block_y=3, block_h=5, spp=1), {"sample_chains": 8}),
-                             ((1, 1), dict(spp=4), {})):
+                             ((1, 1), dict(spp=4), {}),
+                             # 8x4 primary tiles (PrimarySource::map): whole tiles + 3 ragged rows; a block whose rows are 4 tiled + 2 linear,
+                             # several sample slots per launch
+                             ((72, 11), dict(spp=3), {}), ((64, 10), dict(block_y=3, block_h=6, spp=6), {"sample_slots": 3, "sample_chains": 2})):
         sc = C.small_scene("c2", w, h)
         seeds = T.splitmix_seeds(3, kw["spp"] * (1 + kw.get("num_bounces", 5)))
         a, b, st, _ = _compare_traces(sc, w, h, kw, seeds, f"{w}x{h} {kw} {opts}", **opts)
