@@ -857,6 +857,9 @@ constexpr uint32_t KEY_KILLED = SHADE_KEYS - 3, KEY_MISS = SHADE_KEYS - 2, KEY_I
 #ifndef PC_SORT_LEAF
 #define PC_SORT_LEAF 0
 #endif
+#ifndef PC_SHADE_PREFETCH
+#define PC_SHADE_PREFETCH 0
+#endif
 // Rays per thread and tile.  A tile is SHADE_BLOCK * SHADE_RPT consecutive rays; after the sort the CTA's
 // warps PULL 32-ray chunks of the sorted tile from a shared counter, so a warp that drew a cheap material
 // (diffuse) takes the next chunk instead of waiting at the tile's barrier for the warp that drew the
@@ -973,6 +976,18 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
             uint32_t k = KEY_INACTIVE, tri = 0xFFFFFFFFu;
             if (i < n) {
                 k = KEY_MISS;
+#if PC_SHADE_PREFETCH
+                // MEASURED AND REJECTED (profiles/ab_r02o.txt): the shading phase starts every ray with a dependent pair of DRAM
+                // reads -- the ray (for its path index) and then the path record, which sits wherever that index points.  Asking
+                // for both here, into L2 only, so that they arrive while the tile is sorted, made k_shade SLOWER (698 -> 716 us on
+                // config 2, 465 -> 477 us on the 4K frame): the extra load + slot lookup per ray in the sort phase cost more than
+                // the shorter wait returns -- with two tiles per SM the other tile's shading already covers that latency.
+                if (bounce < minBouncesForRR || !PC_SORT_RR) {
+                    const uint32_t pi = (uint32_t)__ldcg(&fb.rays[a][i].dir.w);
+                    const uint32_t ps = oneSlot ? 0u : slotOf(sh.baseA, i);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(fb.paths + (size_t)ps * slotPaths + pi));
+                }
+#endif
                 if (__ldcs(fb.hitFlags + i)) {
                     tri = __ldcs(&fb.hits[i].meta).y;
                     uint32_t node = PC_LDG(sc.matIndex + tri);
