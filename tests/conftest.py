@@ -18,7 +18,7 @@ def _native_built():
     """The CPU tier needs the oracle, the scene compiler and the test-only emulation library."""
     import subprocess
 
-    need = ["polaris_b200/libpolaris_scene.so", "oracle/libpolaris_oracle.so", "tests/emul/libpc_emul.so",
+    need = ["polaris_b200/libpolaris_scene.so", "oracle/libpolaris_oracle.so", "tests/emul/libpc_emul.so", "tests/emul/libpc_emul_popcull.so",
             "polaris_b200/libpolaris_cuda.so"]
     if not all(os.path.exists(os.path.join(ROOT, p)) for p in need):
         subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.build()"], cwd=ROOT, check=True)

@@ -210,3 +210,26 @@ def test_wide_traversal_variant_reproduces_the_golden_vectors(key):
     spp, seeds = int(g["spp"]), g["seeds"]
     emu.trace(T.make_block_request(w, h, spp=spp), seeds)
     assert C.acc_of(emu, _lib.BUF_TRACE_ACCUMULATOR, w, h).tobytes() == g["full_acc"].tobytes()
+
+
+@pytest.mark.parametrize("key", ["c1", "c2", "c3", "c4"])
+def test_pop_culling_variant_reproduces_the_golden_vectors(key):
+    """PC_POP_CULL (stacked far children carry their entry distance and are tested again when popped; measured slower on the
+    GPU and compiled out of the product build): the same device code built for the host returns the golden
+    hit records and the golden full-depth frame bit for bit -- a subtree culled at pop time cannot hold a hit with
+    t <= best -- while visiting no more nodes or triangles than the plain walk."""
+    g = load(key)
+    sc, w, h = scene_for(key, g)
+    emu, plain = C.Emul(sc, w, h, variant="_popcull"), C.Emul(sc, w, h)
+    flags, hits, cnt = emu.intersect(g["rays"], 0)
+    _, _, cnt0 = plain.intersect(g["rays"], 0)
+    assert np.array_equal(flags, g["flags"])
+    hit = g["flags"] == 1
+    assert hits["wuvt"][hit].tobytes() == g["hits"]["wuvt"][hit].tobytes()
+    assert np.array_equal(hits["mesh_instance"][hit], g["hits"]["mesh_instance"][hit]) and np.array_equal(hits["tri_index"][hit], g["hits"]["tri_index"][hit])
+    assert cnt[0] <= cnt0[0] and cnt[1] <= cnt0[1]
+    occ_flags, _, _ = emu.intersect(g["occ_rays"], 1)
+    assert np.array_equal(occ_flags, g["occ_flags"])
+    spp, seeds = int(g["spp"]), g["seeds"]
+    emu.trace(T.make_block_request(w, h, spp=spp), seeds)
+    assert C.acc_of(emu, _lib.BUF_TRACE_ACCUMULATOR, w, h).tobytes() == g["full_acc"].tobytes()
