@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, SHADE_MIN_BLOCKS) k_shade(DScene 
         __syncthreads();  // the previous tile's shared state is no longer in use
         if (tid == 0) { sh.tile = atomicAdd(&ctl->ticket[bounce], 1u); sh.nextChunk = 0u; }
         if (tid < SHADE_KEYS) sh.hist[tid] = 0u;
-        if (sortRays) { sh.binOcc[tid] = 0; sh.binInd[tid] = 0; }  // SORT_BINS == SHADE_BLOCK
+        if (sortRays && tid < SORT_BINS) { sh.binOcc[tid] = 0; sh.binInd[tid] = 0; }  // SORT_BINS <= SHADE_BLOCK
         __syncthreads();
         const uint32_t tile = sh.tile;
         if (tile >= nTiles) break;

@@ -12,7 +12,7 @@
 
 namespace pc {
 
-static_assert(SORT_BINS == SHADE_BLOCK, "k_shade clears one bin per thread");
+static_assert(SORT_BINS <= SHADE_BLOCK, "k_shade clears one bin per thread");
 
 const char *shade_fp_mode() { return PC_SHADE_FP_MODE; }
 
