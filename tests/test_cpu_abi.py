@@ -122,3 +122,21 @@ def test_go_backend_patch_applies_to_the_reference():
         r = subprocess.run(["patch", "--dry-run", "-p1", "-d", "/root/reference"], stdin=f, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "renderer/cuda_backend.go" in r.stdout and "renderer/default.go" in r.stdout
+
+
+def test_go_shim_binds_only_what_the_header_declares():
+    """The cgo package (go/tracer/cuda, go/asset/scene) cannot be compiled in this image; what can be checked is that every
+    C.pc_* function, C.pc_* type and C.PC_* constant it names is declared in include/polaris_cuda.h, so a renamed or removed
+    entry point cannot go unnoticed."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "polaris_cuda.h")).read()
+    declared = set(re.findall(r"\b(pc_[a-z_0-9]+|PC_[A-Z_0-9]+)\b", header))
+    used = set()
+    for dirpath, _, files in os.walk(os.path.join(root, "go")):
+        for f in files:
+            if f.endswith(".go"):
+                used |= set(re.findall(r"\bC\.(pc_[a-z_0-9]+|PC_[A-Z_0-9]+)\b", open(os.path.join(dirpath, f)).read()))
+    assert len(used) >= 20, used  # the shim does bind the tracer interface
+    assert not (used - declared), sorted(used - declared)
