@@ -65,6 +65,10 @@ class Camera:
 
     def update(self):
         pos = np.asarray(self.position, dtype=F)
+        # a LookAt (or position) somebody set since the last update is the new "given" one; our own write-back below is not
+        own = getattr(self, "_own", None)
+        if own is not None and not (np.array_equal(self.look_at, own[0]) and np.array_equal(pos, own[1])):
+            self.look_at_given = np.array(self.look_at, dtype=F)
         d = gt.v_normalize(np.asarray(self.look_at, dtype=F) - pos)
         pitch_axis = gt.v_cross(d, self.up)
         pq = gt.quat_from_axis_angle(pitch_axis, self.pitch)
@@ -72,6 +76,9 @@ class Camera:
         oq = gt.quat_normalize(gt.quat_mul(pq, yq))
         d = gt.quat_rotate(oq, d)
         self.look_at = (pos + np.array([F(c * F(1.0)) for c in d], dtype=F)).astype(F)
+        if self.pitch != 0.0 or self.yaw != 0.0:  # rotated away from the given LookAt: only the written-back one describes the view
+            self.look_at_given = self.look_at.copy()
+        self._own = (self.look_at.copy(), pos.copy())
         self.view_mat = gt.look_at_v(pos, self.look_at, self.up)
         inv = gt.inv4(gt.mul4(self.proj_mat, self.view_mat))
         y_up = F(-1.0) if self.invert_y else F(1.0)

@@ -222,6 +222,25 @@ def test_scene_dump_roundtrip(tmp_path, key):
     assert back.camera.frustrum.tobytes() == sc.camera.frustrum.tobytes()
 
 
+def test_scene_dump_follows_a_moved_camera(tmp_path):
+    """The dump keeps the LookAt the camera was GIVEN -- also after somebody moved the camera and updated it again."""
+    import copy
+    sc = copy.deepcopy(C.small_scene("c1", 64, 64))
+    cam = sc.camera
+    cam.position = (cam.position + np.array([0.25, -0.5, 0.75], F)).astype(F)
+    cam.look_at = np.array([0.1, 0.2, -0.3], F)
+    cam.update()
+    cam.update()  # a second update re-normalises the written-back LookAt, like the interactive renderer does every frame
+    p = tmp_path / "moved.bin"
+    sc.save(p)
+    back = S.Scene.load(p)
+    back.camera.setup_projection(F(1.0))
+    fresh = S.Camera(cam.position.copy(), np.array([0.1, 0.2, -0.3], F), cam.up.copy(), cam.fov)
+    fresh.setup_projection(F(1.0))
+    assert back.camera.frustrum.tobytes() == fresh.frustrum.tobytes()
+    assert np.allclose(back.camera.frustrum, cam.frustrum, atol=1e-6)
+
+
 def test_scene_cache_returns_the_same_scene(tmp_path, monkeypatch):
     """POLARIS_SCENE_CACHE (scenes.build): the second build loads the dump and must be indistinguishable from the first."""
     from polaris_b200 import scenes
